@@ -1,0 +1,131 @@
+"""Generate the committed golden vectors by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+Writes small .npz fixtures next to this file. The reference has no golden vectors or tests of
+its own; these fixtures are outputs of its own functions on seeded synthetic
+inputs and are what pins ``oracle/`` (tests/test_oracle.py) and the CUDA path (tests/test_*_gpu.py).
+"""
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from cy2path_b200.synth import knn_velocity_tpm  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+
+def adata_for(g, ref):
+    return ref.DuckAnnData(g["T"], pd.DataFrame({"root_cells": g["root_cells"], "end_points": g["end_points"]}))
+
+
+def csr_fields(T, prefix="T_"):
+    return {prefix + "indptr": T.indptr, prefix + "indices": T.indices, prefix + "data": T.data,
+            prefix + "n": np.int64(T.shape[0])}
+
+
+def golden_msm(ref, name, n, k, seed, max_iter, variable_degree=False, init="root_cells", tol=1e-5):
+    g = knn_velocity_tpm(n, k=k, seed=seed, variable_degree=variable_degree)
+    ad = adata_for(g, ref)
+    init_p, _ = ref.utils.check_root_init(ad, init=init)
+    stat = g["end_points"] / g["end_points"].sum()  # the reference's own fall-back (utils.py:110-112)
+    sh, shm, conv = ref.sampling.iterate_state_probability(ad, init=init_p, stationary=stat, max_iter=max_iter, tol=tol)
+    np.savez_compressed(os.path.join(HERE, name), **csr_fields(g["T"]), init=np.asarray(init_p, dtype=np.float64),
+                        stationary=stat, history=shm, convergence=np.int64(conv), tol=np.float64(tol),
+                        root_cells=g["root_cells"], end_points=g["end_points"])
+    print(name, shm.shape, "conv", conv)
+
+
+def golden_chains(ref, name, n, k, seed, C, max_iter, variable_degree=False):
+    g = knn_velocity_tpm(n, k=k, seed=seed, variable_degree=variable_degree)
+    ad = adata_for(g, ref)
+    idx, cum = ref.simulation.extract_nonzero_entries(ad)
+    rng = np.random.default_rng(seed + 100)
+    init_states = rng.choice(n, C).astype(np.int32)
+    uniforms = rng.random((C, max_iter - 1))
+    # rounding to 3 decimals can leave the last CDF entry below 1 (reference FIXME simulation.py:48);
+    # keep supplied draws under the row minimum of the final CDF value so the reference itself runs
+    rows_last = np.take_along_axis(cum, (np.maximum((cum > 0).sum(1), 1) - 1)[:, None], 1).ravel()
+    uniforms *= float(rows_last.min())
+    states = np.empty((C, max_iter), dtype=np.int32)
+    probs = np.empty((C, max_iter - 1), dtype=np.float32)
+    real_rand = np.random.rand
+    try:
+        for c in range(C):
+            np.random.rand = lambda m, _c=c: uniforms[_c].copy()
+            s, p = ref.simulation.iterate_markov_chain(ad, max_iter=max_iter, init_state=init_states[c],
+                                                       nonzero_entries=(idx, cum))
+            states[c], probs[c] = s, p
+    finally:
+        np.random.rand = real_rand
+    np.savez_compressed(os.path.join(HERE, name), **csr_fields(g["T"]), idx=idx, cum=cum, init_states=init_states,
+                        uniforms=uniforms, states=states, probs=probs)
+    print(name, idx.shape, states.shape)
+
+
+def golden_fhmm(ref, name, S, L, N, I, restricted, seed, k=6):
+    g = knn_velocity_tpm(N, k=k, seed=seed)
+    ad = adata_for(g, ref)
+    init_p, _ = ref.utils.check_root_init(ad, init="root_cells")
+    stat = g["end_points"] / g["end_points"].sum()
+    _, shm, _ = ref.sampling.iterate_state_probability(ad, init=init_p, stationary=stat, max_iter=I)
+    D = torch.Tensor(shm)  # float32, as infer_dynamics.py:207-211
+    TPM = torch.Tensor(g["T"].toarray())  # dense, as infer_dynamics.py:204
+    torch.manual_seed(seed)
+    model = ref.models.FHMM(S, L, N, I, restricted=restricted, use_gpu=False)
+    params0 = {k_: v.detach().clone().numpy() for k_, v in model.state_dict().items()}
+    with torch.no_grad():
+        pred, joint, hidden = model.forward_model()
+        ref.methods.compute_log_likelihood(model)
+        ll = model.log_likelihood.item()
+    # one epoch with a zero-learning-rate optimiser: parameters stay put, .grad survives
+    model.train(D, TPM=TPM, num_epochs=1, TPM_weight=0.05,
+                optimizer=torch.optim.SGD(model.parameters(), lr=0.0))
+    grads = {"grad_" + k_: p.grad.detach().clone().numpy() for k_, p in model.named_parameters()}
+    terms = dict(loss=model.loss_values[0], divergence=model.divergence_values[0],
+                 likelihood=model.likelihood_values[0], sparsity=model.sparsity_values[0],
+                 orthogonality=model.orthogonality_values[0], regularisation=model.regularisation_values[0],
+                 exclusivity=(model.exclusivity_values[0] if L > 1 else np.nan))
+    # three default-optimiser epochs from the same start (trainer drop-in trajectory)
+    torch.manual_seed(seed)
+    model2 = ref.models.FHMM(S, L, N, I, restricted=restricted, use_gpu=False)
+    model2.train(D, TPM=TPM, num_epochs=3)
+    traj = np.array([model2.loss_values, model2.divergence_values, model2.likelihood_values,
+                     model2.sparsity_values, model2.orthogonality_values,
+                     model2.exclusivity_values if L > 1 else [np.nan] * 3, model2.regularisation_values])
+    params3 = {"after3_" + k_: v.detach().clone().numpy() for k_, v in model2.state_dict().items()}
+    # decoders (next-row f-1) on the trained model
+    with torch.no_grad():
+        model2.forward_model()
+        la, lp = model2.filtering(D)
+        lb, lg = model2.smoothing(D)
+        ld, psi, lmax, best = model2.viterbi(D)
+    np.savez_compressed(
+        os.path.join(HERE, name), **csr_fields(g["T"]), D=D.numpy(), S=S, L=L, N=N, I=I, restricted=restricted,
+        **params0, **grads, **params3, pred=pred.numpy(), joint=joint.numpy(), hidden=hidden.numpy(),
+        log_likelihood=np.float64(ll), term_names=np.array(list(terms.keys())),
+        term_values=np.array(list(terms.values()), dtype=np.float64), weights=np.array([1.0, 0.1, 0.1, 0.05]),
+        traj=traj, log_alpha=la.numpy(), log_probs=lp.numpy(), log_beta=lb.numpy(), log_gamma=lg.numpy(),
+        log_delta=ld.numpy(), psi=psi.numpy(), log_max=lmax.numpy(), best_path=np.array(best, dtype=np.float64))
+    print(name, "loss", terms["loss"], "ll", ll)
+
+
+def main():
+    ref = ref_shim.load()
+    golden_msm(ref, "msm_small.npz", n=400, k=10, seed=11, max_iter=120)
+    golden_msm(ref, "msm_vardeg.npz", n=300, k=12, seed=12, max_iter=80, variable_degree=True, init="uniform")
+    golden_chains(ref, "chains_small.npz", n=400, k=10, seed=11, C=48, max_iter=60)
+    golden_chains(ref, "chains_wide.npz", n=300, k=40, seed=13, C=32, max_iter=40)  # W > 32: multi-chunk search
+    golden_fhmm(ref, "fhmm_restricted.npz", S=4, L=3, N=60, I=25, restricted=True, seed=21)
+    golden_fhmm(ref, "fhmm_unrestricted.npz", S=3, L=2, N=50, I=20, restricted=False, seed=22)
+    golden_fhmm(ref, "fhmm_single_chain.npz", S=5, L=1, N=40, I=15, restricted=True, seed=23)
+
+
+if __name__ == "__main__":
+    main()
