@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the cy2path hot path on B200 (contract in the task statement).
+
+A "step" is one pass of the hot path over one batch of synthetic input of BASELINE.json configs[1]:
+  n = 50,000-cell synthetic kNN velocity TPM (k = 30), 4,096 batched start distributions x 2,000
+  MSM iterations (with the per-iteration cosine distance to the stationary vector), plus 100,000
+  sampled Markov chains x 2,000 steps (with transition probabilities and the per-step histogram).
+metric = MSM simulation cell-iterations/s = n*B*iters / step time (the chain sampling is inside the
+timed step; its own rate is reported under "detail").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+N > 1 is launched by torchrun (one rank per GPU); every rank runs the same per-GPU workload on its own
+start distributions / chains (T replicated, no data-path collective) => weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: n, k, B, iters, chains, chain_len (max_iter), seed
+    "config2": dict(n=50_000, k=30, B=4096, iters=2000, chains=100_000, max_iter=2000, seed=2),
+    "config1": dict(n=3_696, k=30, B=1, iters=1000, chains=0, max_iter=0, seed=1),
+    "config4": dict(n=250_000, k=30, B=4096, iters=1000, chains=0, max_iter=0, seed=4),
+    "tiny": dict(n=5_000, k=30, B=256, iters=50, chains=2_000, max_iter=100, seed=9),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ inputs
+def make_inputs(w, rank):
+    from cy2path_b200.synth import batched_starts, chain_inputs, knn_velocity_tpm, stationary_by_power
+
+    g = knn_velocity_tpm(w["n"], k=w["k"], seed=w["seed"])
+    T = g["T"]
+    stat = stationary_by_power(T, iters=200)
+    X0 = batched_starts(T, w["B"], seed=w["seed"] + 1000 * rank)
+    root = g["root_cells"] / g["root_cells"].sum()
+    init_s = uni = None
+    if w["chains"]:
+        init_s, uni = chain_inputs(T, root, w["chains"], w["max_iter"], seed=w["seed"] + 1000 * rank)
+    return dict(T=T, stat=stat, X0=X0, root=root, end=g["end_points"], root_cells=g["root_cells"], init_s=init_s,
+                uni=uni)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for j, nm in enumerate(names) if any(r[2 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------ CPU leg
+def _cpu_worker(args):
+    """One worker of the CPU reference arm: the reference's own arithmetic (scipy ``x @ T`` loop + scipy cosine,
+    sampling.py:38-45) on a slice of the start distributions."""
+    indptr, indices, data, n, Xs, stat, iters = args
+    import scipy.sparse as sp
+
+    from oracle import msm as omsm
+
+    T = sp.csr_matrix((data, indices, indptr), shape=(n, n))
+    X = np.asarray(Xs, dtype=np.float64)  # [b, n]
+    for _ in range(iters):
+        X = np.asarray(X @ T)
+        for b in range(X.shape[0]):
+            omsm.cosine_distance(X[b], stat)
+    return float(X.sum())
+
+
+def cpu_reference_rate(inp, w, cores, b_per_core, iters, pool=None):
+    """cell-iterations/s of the oracle port (same scipy code path the reference executes) on `cores` processes."""
+    import multiprocessing as mp
+
+    T = inp["T"]
+    jobs = []
+    for c in range(cores):
+        cols = [(c * b_per_core + j) % w["B"] for j in range(b_per_core)]
+        jobs.append((T.indptr, T.indices, T.data, T.shape[0], np.ascontiguousarray(inp["X0"][:, cols].T), inp["stat"],
+                     iters))
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+    t0 = time.perf_counter()
+    if pool is None:
+        _cpu_worker(jobs[0])
+    else:
+        pool.map(_cpu_worker, jobs)
+    dt = time.perf_counter() - t0
+    if own and pool is not None:
+        pool.close()
+    return T.shape[0] * b_per_core * cores * iters / dt, dt
+
+
+def cpu_chain_rate(inp, w, chains=2000):
+    """chain-steps/s of the oracle's C restatement of iterate_markov_chain on one core (bounded sample)."""
+    from oracle import chains as ochains
+    from oracle import fast as ofast
+
+    if not w["chains"]:
+        return None
+    T = inp["T"]
+    idx, cum = ochains.extract_nonzero_entries(T)
+    uni = inp["uni"][:chains] * float(cum.max(1).min())
+    t0 = time.perf_counter()
+    ofast.sample_chains(T, idx, cum, inp["init_s"][:chains], uni)
+    return chains * uni.shape[1] / (time.perf_counter() - t0)
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    inp = make_inputs(w, 0)
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    b_per_core, iters = 8, 25  # bounded sample per step: cores*8 starts x 25 iterations
+    pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+    for _ in range(args.warmup):
+        cpu_reference_rate(inp, w, cores, b_per_core, max(1, iters // 5), pool)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_rate(inp, w, cores, b_per_core, iters, pool)
+    dt = time.perf_counter() - t0
+    if pool is not None:
+        pool.close()
+    value = w["n"] * b_per_core * cores * iters * args.steps / dt
+    sample = f"{cores} processes x {b_per_core} starts x {iters} iterations per step, scipy x@T + cosine"
+    line = {
+        "impl": "reference", "metric": "msm_cell_iterations_per_s", "value": value, "unit": "cell-iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(w, args, 1),
+        "cpu_baseline": {"value": value, "unit": "cell-iterations/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "cell-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(w, args, world):
+    return {"workload": f"{args.workload}: {w['n']}-cell synthetic kNN velocity TPM (k={w['k']}), "
+                        f"{w['B']} start distributions x {w['iters']} iterations"
+                        + (f" + {w['chains']} chains x {w['max_iter']} steps" if w["chains"] else "")
+                        + " per GPU",
+            "n": w["n"], "nnz": w["n"] * w["k"], "B_per_gpu": w["B"], "iters": w["iters"],
+            "chains_per_gpu": w["chains"], "chain_len": w["max_iter"], "parallelism": f"batch-shard x{world}",
+            "l2_policy": "inputs larger than L2 (X0 is %.0f MB per GPU)" % (w["n"] * w["B"] * 4 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import cy2path_b200 as c2p
+    from cy2path_b200 import _lib
+    from cy2path_b200.sampling import get_plan
+    from cy2path_b200.simulation import _tables_device, _walk
+
+    lib = _lib.load()
+    inp = make_inputs(w, rank)
+    T, n, B, iters = inp["T"], w["n"], w["B"], w["iters"]
+    dev = torch.device("cuda", local)
+    plan = get_plan(T)
+    X0_d = torch.from_numpy(inp["X0"]).to(dev)
+    stat_d = torch.from_numpy(inp["stat"]).to(dev)
+    has_chains = bool(w["chains"])
+    if has_chains:
+        idx_d, cum_d = _tables_device(plan)
+        scale = float(cum_d.max(1).values.min())  # keep draws under the smallest final CDF entry (reference FIXME)
+        inp["uni"] *= scale
+        uni_d = torch.from_numpy(inp["uni"]).to(dev)
+        init_d = torch.from_numpy(inp["init_s"]).to(dev)
+
+    prop_ms = []
+
+    def step_device():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = _lib.propagate(plan, X0_d, iters, stationary=stat_d, want_final=True, want_eps=True)
+        e1.record()
+        prop_ms.append((e0, e1))
+        if has_chains:
+            _walk(plan, idx_d, cum_d, init_d, uni_d, want_history_steps=w["max_iter"])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    prop_ms.clear()
+    launches0 = lib.cy2p_launch_count()
+    with ClockSampler(local) as clocks:
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            step_device()
+        t1.record()
+        barrier()
+    launches = lib.cy2p_launch_count() - launches0
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    cell_iters_per_gpu = n * B * iters
+    value = world * cell_iters_per_gpu * args.steps / (ms_total * 1e-3)
+    prop_ms_avg = float(np.mean([a.elapsed_time(b) for a, b in prop_ms]))
+    chain_ms = ms_per_step - prop_ms_avg
+
+    # ---- roofline of the dominant kernel (spmm_gather): algorithmic bytes per launch / mean launch duration
+    tile = int(lib.cy2p_propagate_column_tile(plan.handle, B))
+    tiles = (B + tile - 1) // tile
+    gather_launches = tiles * iters
+    bytes_per_launch = 8 * T.nnz + 4 * (n + 1) + 2 * 4 * n * min(tile, B)  # 8 nnz + 4(n+1) + 8 n b
+    launch_s = prop_ms_avg * 1e-3 / gather_launches
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_per_launch / launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "spmm_gather<4,true>", "bytes_per_launch": bytes_per_launch,
+                "launch_us": launch_s * 1e6, "launches_per_step": gather_launches, "column_tile": tile,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (sustained copy)" if peaks else "fallback 6650 GB/s"}
+
+    # ---- end to end through the public API with host buffers (H2D of T, X0, uniforms; D2H of results)
+    e2e = None
+    if not args.no_e2e:
+        import pandas as pd
+
+        class Adata:
+            pass
+
+        def step_e2e():
+            from cy2path_b200.sampling import clear_plan_cache
+
+            clear_plan_cache()  # the plan (H2D of T, transpose, tables) is rebuilt inside the timed step
+            r = c2p.propagate_batch(T, inp["X0"], iters, stationary=inp["stat"])
+            if has_chains:
+                ad = Adata()
+                ad.obsp, ad.shape, ad.uns = {"T_forward": T}, (n, 0), {}
+                ad.obs = pd.DataFrame({"root_cells": inp["root_cells"], "end_points": inp["end"]})
+                c2p.sample_markov_chains(ad, num_chains=w["chains"], max_iter=w["max_iter"], convergence=w["max_iter"],
+                                         uniforms=inp["uni"], init_states=inp["init_s"])
+            return r
+
+        import cy2path_b200.simulation as sim
+
+        sim.estimate_stationary_state = lambda adata, matrix_key="T_forward": inp["stat"]  # input, not timed work
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = T.nnz * 8 + 4 * (n + 1) + n * B * 4 + n * 8
+        d2h = n * B * 4 + iters * B * 8
+        if has_chains:
+            h2d += w["chains"] * (w["max_iter"] - 1) * 8 + w["chains"] * 4
+            d2h += w["chains"] * w["max_iter"] * 4 + w["chains"] * (w["max_iter"] - 1) * 4 + w["max_iter"] * n * 4
+        e2e = {"value": world * cell_iters_per_gpu * args.steps / float(dt.item()), "unit": "cell-iterations/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": float(dt.item()) / args.steps * 1e3}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb, ci = min(32, B), max(1, int(1.2e9 / (n * min(32, B))))  # ~1.2e9 cell-iterations: 10-30 s of one core
+        rate, secs = cpu_reference_rate(inp, w, 1, cb, ci)
+        cpu = {"value": rate, "unit": "cell-iterations/s", "cores": 1, "kind": "port",
+               "sample": f"1 thread, {cb} starts x {ci} iterations of scipy x@T + cosine ({secs:.1f} s)",
+               "host_cores_available": os.cpu_count()}
+        cr = cpu_chain_rate(inp, w)
+        if cr:
+            cpu["chain_steps_per_s_1core_c_port"] = cr
+
+    if rank == 0:
+        line = {
+            "metric": "msm_cell_iterations_per_s", "value": value, "unit": "cell-iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(w, args, world), "clocks": clocks.summary(), "gpu_launches": int(launches),
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "detail": {"propagate_ms_per_step": prop_ms_avg, "chains_ms_per_step": chain_ms,
+                       "chain_steps_per_s": (world * w["chains"] * (w["max_iter"] - 1) / (chain_ms * 1e-3)
+                                             if has_chains and chain_ms > 0 else None),
+                       "propagate_cell_iterations_per_s": world * cell_iters_per_gpu / (prop_ms_avg * 1e-3)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,238 @@
+"""ctypes binding of the C ABI in include/cy2path_b200.h.
+
+PyTorch is used only for device memory, streams and host<->device copies; every arithmetic
+step of the hot path runs in libcy2path_b200.so. There is NO CPU fallback: if the library is
+missing or no CUDA device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcy2path_b200.so")
+
+OK, ERR_INVALID_ARG, ERR_BAD_CSR, ERR_CDF_OVERSHOOT, ERR_CUDA, ERR_WORKSPACE, ERR_CDF_TABLE = range(7)
+
+# every symbol the header declares (tests check the built library exports all of them)
+SYMBOLS = [
+    "cy2p_abi_version", "cy2p_last_error", "cy2p_launch_count", "cy2p_plan_create", "cy2p_plan_create_host", "cy2p_plan_destroy",
+    "cy2p_plan_info", "cy2p_propagate_ws_bytes", "cy2p_propagate_column_tile", "cy2p_propagate", "cy2p_propagate_rows", "cy2p_cdf_build",
+    "cy2p_sample_chains", "cy2p_chain_history", "cy2p_fhmm_ws_bytes", "cy2p_fhmm_small_floats",
+    "cy2p_fhmm_forward", "cy2p_fhmm_loss_grad",
+]
+
+_lib = None
+_vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
+
+
+class Cy2pError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once). Raises ImportError with build instructions if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found. The CUDA library is required (there is no CPU fallback); build it with "
+            "`python -m cy2path_b200._build` or `python -c 'import __graft_entry__ as g; g.build()'`.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.cy2p_abi_version.restype = _i32
+    lib.cy2p_last_error.restype = ctypes.c_char_p
+    lib.cy2p_launch_count.restype = _i64
+    lib.cy2p_plan_create.argtypes = [_i32, _i64, _vp, _vp, _vp, _i32, _vp, ctypes.POINTER(_vp)]
+    lib.cy2p_plan_create_host.argtypes = lib.cy2p_plan_create.argtypes
+    lib.cy2p_plan_destroy.argtypes = [_vp]
+    lib.cy2p_plan_info.argtypes = [_vp, ctypes.POINTER(_i64)]
+    lib.cy2p_propagate_ws_bytes.argtypes = [_vp, _i32, _i32]
+    lib.cy2p_propagate_ws_bytes.restype = _sz
+    lib.cy2p_propagate_column_tile.argtypes = [_vp, _i32]
+    lib.cy2p_propagate.argtypes = [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]
+    lib.cy2p_propagate_rows.argtypes = [_vp, _vp, _vp, _i32, _i32, _i32, _vp]
+    lib.cy2p_cdf_build.argtypes = [_vp, _vp, _vp, _i32, _vp]
+    lib.cy2p_sample_chains.argtypes = [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]
+    lib.cy2p_chain_history.argtypes = [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]
+    if hasattr(lib, "cy2p_fhmm_forward"):
+        lib.cy2p_fhmm_ws_bytes.argtypes = [_i32, _i32, _i32, _i32]
+        lib.cy2p_fhmm_ws_bytes.restype = _sz
+        lib.cy2p_fhmm_small_floats.argtypes = [_i32, _i32]
+        lib.cy2p_fhmm_small_floats.restype = _i32
+        lib.cy2p_fhmm_forward.argtypes = [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                          _vp, _sz, _vp]
+        lib.cy2p_fhmm_loss_grad.argtypes = [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                                            ctypes.POINTER(ctypes.c_float), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
+    for name in SYMBOLS:
+        fn = getattr(lib, name, None)
+        if fn is not None and name not in ("cy2p_last_error", "cy2p_propagate_ws_bytes", "cy2p_fhmm_ws_bytes",
+                                           "cy2p_fhmm_small_floats", "cy2p_abi_version", "cy2p_launch_count"):
+            fn.restype = _i32
+    _lib = lib
+    return lib
+
+
+def check(status):
+    """Map a C status to the exception type the reference raises in the same situation."""
+    if status == OK:
+        return
+    msg = load().cy2p_last_error().decode("utf-8", "replace")
+    if status in (ERR_CDF_OVERSHOOT, ERR_CDF_TABLE):
+        raise IndexError(msg)  # reference: simulation.py:78-81 / :43-46
+    if status in (ERR_INVALID_ARG, ERR_BAD_CSR):
+        raise ValueError(msg)
+    raise Cy2pError(f"status {status}: {msg}")
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise Cy2pError("cy2path_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+    return torch
+
+
+def stream_ptr(device=None):
+    torch = _torch()
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class Plan:
+    """Device-resident T and T^T for one transition matrix on one device (cy2p_plan)."""
+
+    def __init__(self, T, device=None):
+        torch = _torch()
+        lib = load()
+        import scipy.sparse as sp
+
+        if not sp.issparse(T):
+            T = sp.csr_matrix(T)
+        T = T.tocsr()
+        self.n = int(T.shape[0])
+        if T.shape[0] != T.shape[1]:
+            raise ValueError("transition matrix must be square")
+        self.nnz = int(T.nnz)
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        indptr = np.ascontiguousarray(T.indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(T.indices, dtype=np.int32)
+        data = np.ascontiguousarray(T.data, dtype=np.float32)
+        handle = _vp(0)
+        with torch.cuda.device(self.device):
+            check(lib.cy2p_plan_create_host(self.n, self.nnz, indptr.ctypes.data, indices.ctypes.data,
+                                            data.ctypes.data, self.device.index, stream_ptr(self.device),
+                                            ctypes.byref(handle)))
+        self.handle = handle
+        info = (_i64 * 8)()
+        check(lib.cy2p_plan_info(self.handle, info))
+        self.max_in_degree, self.max_out_degree, self.W = int(info[2]), int(info[3]), int(info[4])
+        self.bytes_owned = int(info[7])
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and _lib is not None:
+                _lib.cy2p_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def propagate(plan, X0, iters, stationary=None, want_final=True, history_stride=0, want_eps=False):
+    """Run cy2p_propagate. X0: cuda float32 [n, B] (or [n]). Returns dict(final, history, eps) of cuda tensors."""
+    torch = _torch()
+    lib = load()
+    squeeze = X0.dim() == 1
+    X0 = X0.reshape(plan.n, -1).contiguous()
+    assert X0.dtype == torch.float32 and X0.is_cuda
+    B = X0.shape[1]
+    dev = X0.device
+    with torch.cuda.device(dev):
+        st = None
+        if stationary is not None:
+            st = torch.as_tensor(np.asarray(stationary, dtype=np.float64) if not torch.is_tensor(stationary)
+                                 else stationary, dtype=torch.float64, device=dev).contiguous()
+        final = torch.empty_like(X0) if want_final else None
+        hist = None
+        if history_stride:
+            slots = (iters + history_stride - 1) // history_stride
+            hist = torch.empty((max(slots, 1), plan.n, B), dtype=torch.float32, device=dev)
+        eps = torch.empty((iters, B), dtype=torch.float64, device=dev) if want_eps else None
+        ws_bytes = lib.cy2p_propagate_ws_bytes(plan.handle, B, iters)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.cy2p_propagate(plan.handle, ptr(X0), B, iters, ptr(st), ptr(final), ptr(hist),
+                                 max(history_stride, 1), ptr(eps), ptr(ws), ws_bytes, stream_ptr(dev)))
+    if squeeze:
+        final = final.reshape(-1) if final is not None else None
+        hist = hist.reshape(hist.shape[0], plan.n) if hist is not None else None
+        eps = eps.reshape(-1) if eps is not None else None
+    return {"final": final, "history": hist, "eps": eps}
+
+
+# ------------------------------------------------------------------------------------------ K3 (FHMM)
+def _fhmm_ws(S, L, N, I, dev):
+    torch = _torch()
+    nbytes = load().cy2p_fhmm_ws_bytes(S, L, N, I)
+    if nbytes == 0:
+        raise ValueError("unsupported model size (supported: S <= 64, L <= 16, S*L <= 256)")
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev), nbytes
+
+
+def fhmm_forward(theta_pi, theta_w, theta_E, theta_A, num_iters, restricted, want_pred=True, want_joint=False):
+    """cy2p_fhmm_forward on cuda float32 parameter tensors. Returns dict of cuda tensors:
+    pred [I,N] | None, hidden [I,S,L], joint [I,S,L,N] | None, log_E [S,Le,N], log_pi, log_w, log_A, log_A_mix."""
+    torch = _torch()
+    lib = load()
+    S, L = theta_pi.shape
+    Le, N = theta_E.shape[1], theta_E.shape[2]
+    I = int(num_iters)
+    dev = theta_pi.device
+    tp, tw, tE, tA = (t.detach().contiguous().float() for t in (theta_pi, theta_w, theta_E, theta_A))
+    with torch.cuda.device(dev):
+        ws, nbytes = _fhmm_ws(S, L, N, I, dev)
+        pred = torch.empty((I, N), dtype=torch.float32, device=dev) if want_pred else None
+        hidden = torch.empty((I, S, L), dtype=torch.float32, device=dev)
+        joint = torch.empty((I, S, L, N), dtype=torch.float32, device=dev) if want_joint else None
+        logE = torch.empty((S, Le, N), dtype=torch.float32, device=dev)
+        small = torch.empty(lib.cy2p_fhmm_small_floats(S, L), dtype=torch.float32, device=dev)
+        check(lib.cy2p_fhmm_forward(S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE), ptr(tA), ptr(pred),
+                                    ptr(hidden), ptr(joint), ptr(logE), ptr(small), ptr(ws), nbytes, stream_ptr(dev)))
+    o = 0
+    log_pi = small[o:o + S * L].view(S, L); o += S * L
+    log_w = small[o:o + L]; o += L
+    log_A = small[o:o + L * S * S].view(L, S, S); o += L * S * S
+    log_A_mix = small[o:o + S * S].view(S, S)
+    return {"pred": pred, "hidden": hidden, "joint": joint, "log_E": logE, "log_pi": log_pi, "log_w": log_w,
+            "log_A": log_A, "log_A_mix": log_A_mix}
+
+
+TERM_NAMES = ("loss", "divergence", "log_likelihood", "sparsity", "orthogonality", "exclusivity", "regularisation")
+
+
+def fhmm_loss_grad(plan, theta_pi, theta_w, theta_E, theta_A, D, restricted, weights, out=None):
+    """cy2p_fhmm_loss_grad: one epoch's forward + loss + analytic gradients.
+    weights = (sparsity, exclusivity, orthogonality, TPM). Returns (terms [8] cuda, (g_pi, g_w, g_E, g_A))."""
+    torch = _torch()
+    lib = load()
+    S, L = theta_pi.shape
+    N = theta_E.shape[2]
+    I = int(D.shape[0])
+    dev = theta_pi.device
+    tp, tw, tE, tA = (t.detach().contiguous() for t in (theta_pi, theta_w, theta_E, theta_A))
+    assert D.is_cuda and D.dtype == torch.float32 and D.is_contiguous() and D.shape[1] == N
+    with torch.cuda.device(dev):
+        if out is None:
+            ws, nbytes = _fhmm_ws(S, L, N, I, dev)
+            out = {"ws": ws, "nbytes": nbytes, "terms": torch.empty(8, dtype=torch.float32, device=dev),
+                   "g": tuple(torch.empty_like(t) for t in (tp, tw, tE, tA))}
+        hw = (ctypes.c_float * 4)(*[float(x) for x in weights])
+        g = out["g"]
+        check(lib.cy2p_fhmm_loss_grad(plan.handle, S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE),
+                                      ptr(tA), ptr(D), hw, ptr(out["terms"]), ptr(g[0]), ptr(g[1]), ptr(g[2]),
+                                      ptr(g[3]), ptr(out["ws"]), out["nbytes"], stream_ptr(dev)))
+    return out["terms"], g, out

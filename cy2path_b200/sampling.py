@@ -1,0 +1,151 @@
+"""Drop-in mirror of cy2path/sampling.py — MSM state-probability simulation on the B200.
+
+Same function names, arguments, return values and ``adata.uns`` keys as the reference
+(sampling.py:13-124). The product ``x @ T`` and the cosine distance to the stationary vector run in
+libcy2path_b200.so (csrc/propagate.cu); the host keeps only the argument checks, the convergence-cut
+bookkeeping (a list scan over ``max_iter`` numbers) and the float64 export the reference promises.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from . import _lib
+from .utils import check_root_init, check_TPM, estimate_stationary_state
+
+logger = logging.getLogger("cy2path_b200")
+
+_PLAN_CACHE: dict = {}
+
+
+def get_plan(T, device=None):
+    """Plan (device copy of T, T^T, tables) for a scipy matrix, cached per matrix object.
+
+    The cache key includes the array addresses, nnz and a strided checksum of the values, so an
+    in-place edit of T rebuilds the plan."""
+    import torch
+
+    dev = torch.cuda.current_device() if device is None else device
+    data = np.asarray(T.data)
+    stride = max(1, data.size // 65536)
+    key = (id(T), dev, T.shape, int(T.nnz), data.ctypes.data, T.indices.ctypes.data,
+           float(data[::stride].sum(dtype=np.float64)))
+    hit = _PLAN_CACHE.get(id(T))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    plan = _lib.Plan(T, device=dev)
+    if len(_PLAN_CACHE) >= 4:
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    _PLAN_CACHE[id(T)] = (key, plan)
+    return plan
+
+
+def clear_plan_cache():
+    _PLAN_CACHE.clear()
+
+
+def check_convergence_criteria(eps_history, tol=1e-5):
+    """reference sampling.py:13-25: (last i with |eps[i+1]-eps[i]| > tol) + 2, ``None`` if there is none."""
+    eps = np.asarray(eps_history, dtype=np.float64)
+    if eps.size < 2:
+        return None
+    above = np.nonzero(np.abs(np.diff(eps)) > tol)[0]
+    if above.size == 0:
+        return None
+    return int(above[-1]) + 2
+
+
+def batch_convergence(eps, tol, max_iter):
+    """check_convergence_criteria + the None / >= max_iter -> max_iter mapping (sampling.py:48-57), per column."""
+    eps = np.asarray(eps, dtype=np.float64)
+    if eps.shape[0] < 2:
+        return np.full(eps.shape[1], max_iter, dtype=np.int64)
+    above = np.abs(np.diff(eps, axis=0)) > tol  # [iters-1, B]
+    last = above.shape[0] - 1 - np.argmax(above[::-1], axis=0)
+    conv = np.where(above.any(axis=0), last + 2, max_iter)
+    return np.where(conv < max_iter, conv, max_iter).astype(np.int64)
+
+
+def iterate_state_probability(adata, matrix_key="T_forward", init=None, stationary=None, max_iter=1000, tol=1e-5):
+    """reference sampling.py:29-60. Returns (state_history, state_history_max_iter, convergence_check);
+    histories are float64 host arrays as in the reference (values are fp32-computed on the device)."""
+    import torch
+
+    T = adata.obsp[matrix_key]
+    plan = get_plan(T)
+    n = plan.n
+    init64 = np.asarray(init, dtype=np.float64).reshape(n)
+    dev = plan.device
+    x0 = torch.from_numpy(init64.astype(np.float32)).to(dev, non_blocking=True)
+    out = _lib.propagate(plan, x0, int(max_iter), stationary=stationary, want_final=False, history_stride=1,
+                         want_eps=True)
+    state_history_max_iter = np.empty((max_iter, n), dtype=np.float64)
+    if max_iter > 0:
+        state_history_max_iter[:] = out["history"].cpu().numpy()
+        state_history_max_iter[0] = init64  # row 0 is the caller's start distribution verbatim (sampling.py:39)
+    eps_history = out["eps"].cpu().numpy() if max_iter > 0 else np.empty(0)
+
+    convergence_check = check_convergence_criteria(eps_history, tol=tol)
+    if isinstance(convergence_check, int) and convergence_check < max_iter:
+        logger.info("Tolerance reached after {} iterations of {}.".format(convergence_check, max_iter))
+    else:
+        logger.warning("Max number ({}) of iterations reached.".format(max_iter))
+        convergence_check = max_iter
+    state_history = state_history_max_iter[:convergence_check]
+    return state_history, state_history_max_iter, convergence_check
+
+
+def propagate_batch(adata_or_T, X0, iters, stationary=None, matrix_key="T_forward", tol=1e-5, return_device=False):
+    """Batched form of the same simulation (BASELINE configs 2/4): B start distributions at once.
+
+    X0: [n, B] float32 (numpy or cuda tensor), cell-major. Returns dict with ``final`` [n, B] and, when
+    ``stationary`` is given, ``eps`` [iters, B] float64 and ``convergence`` [B] (the per-start cut of
+    reference sampling.py:48-57). The full [iters, n, B] history is not materialised (1.6 PB at config 2)."""
+    import torch
+
+    T = adata_or_T.obsp[matrix_key] if hasattr(adata_or_T, "obsp") else adata_or_T
+    plan = get_plan(T)
+    if torch.is_tensor(X0):
+        x0 = X0.to(plan.device, dtype=torch.float32)
+    else:
+        host = torch.from_numpy(np.ascontiguousarray(X0, dtype=np.float32))
+        x0 = host.pin_memory().to(plan.device, non_blocking=True)
+    out = _lib.propagate(plan, x0, int(iters), stationary=stationary, want_final=True, history_stride=0,
+                         want_eps=stationary is not None)
+    res = {"final": out["final"] if return_device else out["final"].cpu().numpy()}
+    if out["eps"] is not None:
+        eps = out["eps"].cpu().numpy()
+        res["eps"] = eps
+        conv = batch_convergence(eps, tol, iters)
+        res["convergence"] = conv
+    return res
+
+
+def sample_state_probability(data, matrix_key="T_forward", recalc_matrix=False, self_transitions=False,
+                             init="root_cells", max_iter=1000, tol=1e-5, copy=False):
+    """reference sampling.py:64-124 — same checks, same ``adata.uns['state_probability_sampling']`` keys."""
+    adata = data.copy() if copy else data
+    check_TPM(adata, matrix_key=matrix_key, recalc_matrix=recalc_matrix, self_transitions=self_transitions)
+    init_state_probability, init_type = check_root_init(adata, init=init)
+    stationary_state_probability = estimate_stationary_state(adata, matrix_key=matrix_key)
+    state_history, state_history_max_iter, convergence_check = iterate_state_probability(
+        adata, matrix_key=matrix_key, init=init_state_probability, stationary=stationary_state_probability,
+        max_iter=max_iter, tol=tol)
+    adata.uns["state_probability_sampling"] = {
+        "state_history": state_history,
+        "state_history_max_iter": state_history_max_iter,
+        "init_state_probability": init_state_probability,
+        "stationary_state_probability": stationary_state_probability,
+        "sampling_params": {
+            "recalc_matrix": recalc_matrix,
+            "self_transitions": self_transitions,
+            "init_type": init_type,
+            "max_iter": max_iter,
+            "convergence": convergence_check,
+            "tol": tol,
+            "copy": copy,
+        },
+    }
+    if copy:
+        return adata

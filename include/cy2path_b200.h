@@ -1,0 +1,146 @@
+/* cy2path_b200 — C ABI of the B200-native hot path of cy2path.
+ *
+ * The reference (aron0093/cy2path) has no FFI/plugin interface: its boundary is a Python
+ * function API over AnnData. This header is the C-ABI that sits directly
+ * underneath that API; each entry point names the reference function it replaces. The
+ * Python mirror of the reference API (cy2path_b200/{sampling,simulation,models}) binds these
+ * symbols with ctypes (cy2path_b200/_lib.py); INTEGRATION.md shows the stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types cross the boundary
+ *  - pointers named d_* are DEVICE pointers on the plan's device, h_* are HOST pointers
+ *  - every function returns an int32 status (CY2P_OK == 0); no exceptions, no aborts;
+ *    cy2p_last_error() returns a thread-local message for the last failure
+ *  - kernels never allocate: work space comes from the caller (cy2p_*_ws_bytes); only
+ *    cy2p_plan_create allocates (plan-owned, freed by cy2p_plan_destroy)
+ *  - stream is a cudaStream_t passed as void*; all work is enqueued on it (functions that
+ *    must return a host value synchronise that stream and say so)
+ *  - re-entrant; the only globals are the thread-local error string and the launch counter;
+ *    one plan per (T, device)
+ */
+#ifndef CY2PATH_B200_H
+#define CY2PATH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CY2P_ABI_VERSION 1
+
+enum cy2p_status {
+    CY2P_OK = 0,
+    CY2P_ERR_INVALID_ARG = 1,   /* null pointer, negative size, misaligned buffer           */
+    CY2P_ERR_BAD_CSR = 2,       /* indptr not monotone / column index out of range          */
+    CY2P_ERR_CDF_OVERSHOOT = 3, /* a uniform exceeded the last CDF entry of a row (the      */
+                                /* reference raises IndexError at simulation.py:78-81)      */
+    CY2P_ERR_CUDA = 4,          /* a CUDA call failed; message carries cudaGetErrorString   */
+    CY2P_ERR_WORKSPACE = 5,     /* caller's work space too small                            */
+    CY2P_ERR_CDF_TABLE = 6      /* a row stores more entries than the table width W (the    */
+                                /* reference raises IndexError at simulation.py:43-46)      */
+};
+
+typedef struct cy2p_plan cy2p_plan;
+
+int32_t cy2p_abi_version(void);
+const char *cy2p_last_error(void);
+/* Number of kernels of this library launched so far by the process (bench.py's gpu_launches). */
+int64_t cy2p_launch_count(void);
+
+/* ---- plan: device-resident T (CSR), T^T (CSR, stable: sources ascending), packed (col,val) ----
+ * Replaces the implicit ``adata.obsp[matrix_key]`` operand of sampling.py:40-42 and the T.T CSC
+ * view scipy builds per call. Validates the CSR. Synchronises `stream` (returns validation). */
+int32_t cy2p_plan_create(int32_t n, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
+                         const float *d_data, int32_t device, void *stream, cy2p_plan **out);
+/* Same, from host arrays (copies H2D inside). */
+int32_t cy2p_plan_create_host(int32_t n, int64_t nnz, const int32_t *h_indptr, const int32_t *h_indices,
+                              const float *h_data, int32_t device, void *stream, cy2p_plan **out);
+int32_t cy2p_plan_destroy(cy2p_plan *plan);
+/* info[0]=n info[1]=nnz info[2]=max in-degree info[3]=max out-degree (stored) info[4]=CDF table width W
+ * info[5]=device info[6]=number of row blocks of the staged kernel info[7]=bytes of device memory owned */
+int32_t cy2p_plan_info(const cy2p_plan *plan, int64_t info[8]);
+
+/* ---- K1: MSM state-probability propagation  X <- X . T, `iters` times ----------------------
+ * Replaces iterate_state_probability's loop (sampling.py:38-45): the product (:40-42) and the
+ * cosine distance to the stationary vector (:44-45), for B start distributions at once.
+ *   d_X0        [n][B] float32, cell-major (row = cell, B contiguous);  B == 1 is the reference's case
+ *   d_stationary[n] float64 or NULL (then d_eps must be NULL)
+ *   d_Xfinal    [n][B] float32: the iterate after `iters` updates (may be NULL if history covers it)
+ *   d_history   NULL, or [ceil(iters/history_stride)][n][B] float32: row h holds the iterate BEFORE
+ *               update h*history_stride (history_stride==1 reproduces state_history_max_iter)
+ *   d_eps       NULL, or [iters][B] float64: eps[i][b] = 1 - cos(x_{i+1}[:,b], stationary), clipped [0,2]
+ *   d_ws        work space of at least cy2p_propagate_ws_bytes(plan, B, iters) bytes, 256-byte aligned
+ * Arithmetic: fp32 products and row sums in ascending source order (the order scipy's csc_matvec
+ * adds them, there in float64); eps dot products accumulate in float64. */
+size_t cy2p_propagate_ws_bytes(const cy2p_plan *plan, int32_t B, int32_t iters);
+/* Width of the column tiles cy2p_propagate carries through all iterations (sized to stay L2-resident). */
+int32_t cy2p_propagate_column_tile(const cy2p_plan *plan, int32_t B);
+int32_t cy2p_propagate(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t iters,
+                       const double *d_stationary, float *d_Xfinal, float *d_history,
+                       int32_t history_stride, double *d_eps, void *d_ws, size_t ws_bytes, void *stream);
+
+/* Row-partitioned variant (BASELINE config 5): computes only destination rows [row_begin,row_end)
+ * of one update, Y[row_begin:row_end, :] = (X . T)[row_begin:row_end, :], reading the whole X.
+ * The caller (cy2path_b200/dist.py) all-gathers the slices between iterations. */
+int32_t cy2p_propagate_rows(cy2p_plan *plan, const float *d_X, float *d_Y, int32_t B,
+                            int32_t row_begin, int32_t row_end, void *stream);
+
+/* ---- K0/K2: chain sampling ------------------------------------------------------------------
+ * cy2p_cdf_build replaces extract_nonzero_entries (simulation.py:15-53): idx int32 [n][W] and
+ * cum float32 [n][W] = round3(float32 sequential cumsum of the row), zero padded; W from plan_info.
+ * Bit-exact with the reference (fp32 adds in storage order, rint(x*1000)/1000 in fp32, no FMA). */
+int32_t cy2p_cdf_build(const cy2p_plan *plan, int32_t *d_idx, float *d_cum, int32_t W, void *stream);
+
+/* cy2p_sample_chains replaces the joblib fan-out of iterate_markov_chain (simulation.py:57-87,
+ * :133-153) given the uniforms each chain consumes:
+ *   d_uniforms [C][steps] float64, d_init_state [C] int32
+ *   d_states   [C][steps+1] int32,  d_probs [C][steps] float32 (T[prev,next], duplicates summed)
+ *   d_err      [4] int32 device scratch: on CDF overshoot {1, chain, step, state}
+ * j = first index with (double)r <= (double)cum[state][j]  (numpy>=2 promotion), bit-exact paths.
+ * Synchronises `stream` and returns CY2P_ERR_CDF_OVERSHOOT if any chain overshot. */
+int32_t cy2p_sample_chains(const cy2p_plan *plan, const int32_t *d_idx, const float *d_cum, int32_t W,
+                           const int32_t *d_init_state, const double *d_uniforms, int64_t C, int32_t steps,
+                           int32_t *d_states, float *d_probs, int32_t *d_err, void *stream);
+
+/* Empirical state history (simulation.py:156-162): hist[k][i] = float32(count_k(i) / C) for the
+ * first `steps1` columns of d_states [C][ld_states]; unvisited entries are 0 (the reference leaves
+ * them uninitialised). d_counts is int32 scratch [steps1][n]. */
+int32_t cy2p_chain_history(const int32_t *d_states, int64_t C, int32_t ld_states, int32_t steps1, int32_t n,
+                           int32_t *d_counts, float *d_hist, void *stream);
+
+/* ---- K3: factorial latent dynamic model (FHMM) ------------------------------------------------
+ * cy2p_fhmm_forward replaces FHMM.forward_model + log_transform_params (_FHMM.py:84-150,
+ * methods.py:6-25). All tensors float32 device, C-contiguous:
+ *   theta_pi [S][L], theta_w [L], theta_E [S][Le][N] (Le = 1 if restricted else L), theta_A [L][S][S]
+ *   d_pred   [I][N] or NULL;  d_hidden [I][S][L];  d_joint [I][S][L][N] or NULL (4 GB at config 3)
+ *   d_logE   [S][Le][N] out: log-softmax of theta_E (kept for the loss pass);
+ *   d_small  out, [cy2p_fhmm_small_floats(S,L)] floats: log_pi, log_w, log_A, log_A_mix (see fhmm.cu)
+ *   d_ws     >= cy2p_fhmm_ws_bytes(S,L,N,I) bytes */
+size_t cy2p_fhmm_ws_bytes(int32_t S, int32_t L, int32_t N, int32_t I);
+int32_t cy2p_fhmm_small_floats(int32_t S, int32_t L);
+int32_t cy2p_fhmm_forward(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted,
+                          const float *theta_pi, const float *theta_w, const float *theta_E,
+                          const float *theta_A, float *d_pred, float *d_hidden, float *d_joint,
+                          float *d_logE, float *d_small, void *d_ws, size_t ws_bytes, void *stream);
+
+/* cy2p_fhmm_loss_grad replaces one epoch's forward + loss + loss.backward() of trainer.train
+ * (trainer.py:134-196) and compute_log_likelihood (methods.py:28-40):
+ *   d_D      [I][N] float32 simulation history;  plan carries T (sparse) for the exclusivity and
+ *            TPM regularisers (the reference multiplies by a densified T, trainer.py:175,190)
+ *   weights  host float[4] = {sparsity, exclusivity, orthogonality, TPM}
+ *   d_terms  [8] float32 out: loss, divergence, log_likelihood, sparsity, orthogonality,
+ *            exclusivity, regularisation, (reserved)
+ *   d_g*     gradients of `loss` w.r.t. the four unnormalised parameters (same shapes) */
+int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted,
+                            const float *theta_pi, const float *theta_w, const float *theta_E,
+                            const float *theta_A, const float *d_D, const float *h_weights,
+                            float *d_terms, float *d_gpi, float *d_gw, float *d_gE, float *d_gA,
+                            void *d_ws, size_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CY2PATH_B200_H */

@@ -1,0 +1,176 @@
+"""GPU parity tests for K1 (MSM propagation) — CUDA path through the C ABI vs oracle and golden vectors.
+
+Parity bar (BASELINE north_star): max-abs <= 1e-5 and relative L1 <= 1e-6 on every stored iterate,
+identical convergence index.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import fast as ofast
+from oracle import msm as omsm
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS, REL_L1 = 1e-5, 1e-6
+
+
+class Duck:
+    def __init__(self, T, root=None, end=None):
+        self.obsp = {"T_forward": T}
+        self.shape = (T.shape[0], 0)
+        self.obs = pd.DataFrame({"root_cells": root, "end_points": end}) if root is not None else pd.DataFrame()
+        self.uns = {}
+
+    def copy(self):
+        import copy
+
+        return copy.deepcopy(self)
+
+
+def _assert_close(a, b):
+    assert np.abs(np.asarray(a, dtype=np.float64) - b).max() <= MAX_ABS
+    assert omsm.rel_l1(a, b) <= REL_L1
+
+
+@pytest.mark.parametrize("name", ["msm_small.npz", "msm_vardeg.npz"])
+def test_history_matches_reference_golden(golden, name):
+    import cy2path_b200 as c2p
+
+    g = golden(name)
+    ad = Duck(g["T"])
+    sh, shm, conv = c2p.iterate_state_probability(ad, init=g["init"], stationary=g["stationary"],
+                                                  max_iter=g["history"].shape[0], tol=float(g["tol"]))
+    assert shm.dtype == np.float64 and shm.shape == g["history"].shape
+    assert conv == int(g["convergence"])
+    assert sh.shape[0] == conv
+    for i in range(shm.shape[0]):
+        _assert_close(shm[i], g["history"][i])
+    assert np.array_equal(shm[0], g["init"])
+
+
+def test_config1_shape_full_history_vs_oracle():
+    """BASELINE config 1: 3,696 cells, k=30, 1,000 iterations from the root prior."""
+    import cy2path_b200 as c2p
+    from cy2path_b200.synth import knn_velocity_tpm
+
+    g = knn_velocity_tpm(3696, k=30, seed=1)
+    init = g["root_cells"] / g["root_cells"].sum()
+    stat = g["end_points"] / g["end_points"].sum()
+    _, ref_hist, ref_conv, ref_eps = omsm.iterate_state_probability(g["T"], init, stat, max_iter=1000)
+    ad = Duck(g["T"])
+    _, hist, conv = c2p.iterate_state_probability(ad, init=init, stationary=stat, max_iter=1000)
+    assert conv == ref_conv
+    assert np.abs(hist - ref_hist).max() <= MAX_ABS
+    worst = max(omsm.rel_l1(hist[i], ref_hist[i]) for i in range(0, 1000, 7))
+    assert worst <= REL_L1
+    # mass conservation / non-negativity (size-independent properties)
+    assert np.abs(hist.sum(1) - 1).max() <= 1e-5 and hist.min() >= 0
+
+
+@pytest.mark.parametrize("B,iters", [(1, 5), (3, 4), (4, 6), (32, 9), (128, 7), (132, 5), (384, 3)])
+def test_batched_matches_oracle_and_equals_looped(B, iters):
+    import torch
+
+    from cy2path_b200 import _lib
+    from cy2path_b200.sampling import get_plan
+    from cy2path_b200.synth import batched_starts, knn_velocity_tpm
+
+    g = knn_velocity_tpm(700, k=12, seed=5, variable_degree=(B % 2 == 1))
+    T = g["T"]
+    X0 = batched_starts(T, B, seed=3)
+    stat = g["end_points"] / g["end_points"].sum()
+    ref = ofast.propagate_batch(T, X0, iters)
+    plan = get_plan(T)
+    out = _lib.propagate(plan, torch.from_numpy(X0).cuda(), iters, stationary=stat, want_eps=True)
+    got = out["final"].cpu().numpy()
+    _assert_close(got, ref)
+    # eps against the oracle's definition, float64 dots
+    Xd = np.asarray(X0, dtype=np.float64)
+    eps_ref = np.empty((iters, B))
+    for i in range(iters):
+        Xd = ofast.propagate_batch(T, Xd, 1)
+        eps_ref[i] = [omsm.cosine_distance(Xd[:, b], stat) for b in range(B)]
+    assert np.abs(out["eps"].cpu().numpy() - eps_ref).max() <= 1e-6
+    # batched == looped single starts, bit for bit (same kernel arithmetic per column family)
+    if B <= 4:
+        for b in range(B):
+            one = _lib.propagate(plan, torch.from_numpy(np.ascontiguousarray(X0[:, b])).cuda(), iters)
+            assert np.abs(one["final"].cpu().numpy() - got[:, b]).max() <= 1e-7
+
+
+def test_history_stride_and_linearity():
+    import torch
+
+    from cy2path_b200 import _lib
+    from cy2path_b200.sampling import get_plan
+    from cy2path_b200.synth import batched_starts, knn_velocity_tpm
+
+    g = knn_velocity_tpm(500, k=8, seed=6)
+    plan = get_plan(g["T"])
+    X0 = torch.from_numpy(batched_starts(g["T"], 8, seed=1)).cuda()
+    out = _lib.propagate(plan, X0, 10, history_stride=3)
+    h = out["history"].cpu().numpy()  # iterates before updates 0, 3, 6, 9
+    assert h.shape == (4, 500, 8)
+    ref = np.asarray(X0.cpu().numpy(), dtype=np.float64)
+    for it in range(10):
+        if it % 3 == 0:
+            _assert_close(h[it // 3], ref)
+        ref = ofast.propagate_batch(g["T"], ref, 1)
+    _assert_close(out["final"].cpu().numpy(), ref)
+    # linearity: propagate(a*x + b*y) == a*propagate(x) + b*propagate(y)
+    a, b = 0.3, 0.7
+    mix = (a * X0[:, :4] + b * X0[:, 4:]).contiguous()
+    pm = _lib.propagate(plan, mix, 6)["final"].cpu().numpy()
+    ps = _lib.propagate(plan, X0, 6)["final"].cpu().numpy()
+    assert np.abs(pm - (a * ps[:, :4] + b * ps[:, 4:])).max() <= 1e-6
+
+
+def test_row_partition_equals_full_update():
+    """Virtual ranks on one GPU: the row-partitioned update (config 5) tiles to the full update."""
+    import ctypes
+
+    import torch
+
+    from cy2path_b200 import _lib
+    from cy2path_b200.sampling import get_plan
+    from cy2path_b200.synth import batched_starts, knn_velocity_tpm
+
+    g = knn_velocity_tpm(900, k=10, seed=7)
+    plan = get_plan(g["T"])
+    for B in (1, 8):
+        X = torch.from_numpy(batched_starts(g["T"], B, seed=2)).cuda()
+        full = _lib.propagate(plan, X, 1)["final"]
+        Y = torch.zeros_like(X)
+        bounds = [0, 200, 455, 900]
+        for r0, r1 in zip(bounds[:-1], bounds[1:]):
+            _lib.check(_lib.load().cy2p_propagate_rows(plan.handle, _lib.ptr(X), _lib.ptr(Y), B, r0, r1,
+                                                       _lib.stream_ptr()))
+        assert torch.equal(Y, full)
+
+
+def test_bad_csr_and_workspace_errors():
+    import scipy.sparse as sp
+
+    from cy2path_b200 import _lib
+
+    T = sp.csr_matrix(np.eye(4, dtype=np.float32))
+    T.indices = T.indices.copy()
+    T.indices[2] = 9
+    with pytest.raises(ValueError):
+        _lib.Plan(T)
+
+
+def test_drop_in_wrapper_keys():
+    import cy2path_b200 as c2p
+    from cy2path_b200.synth import knn_velocity_tpm
+
+    g = knn_velocity_tpm(600, k=10, seed=8)
+    ad = Duck(g["T"], g["root_cells"], g["end_points"])
+    c2p.sample_state_probability(ad, max_iter=50)
+    u = ad.uns["state_probability_sampling"]
+    assert set(u) == {"state_history", "state_history_max_iter", "init_state_probability",
+                      "stationary_state_probability", "sampling_params"}
+    assert set(u["sampling_params"]) == {"recalc_matrix", "self_transitions", "init_type", "max_iter", "convergence",
+                                         "tol", "copy"}
+    assert u["state_history_max_iter"].shape == (50, 600)
