@@ -31,6 +31,8 @@ WORKLOADS = {
     "config1": dict(n=3_696, k=30, B=1, iters=1000, chains=0, max_iter=0, seed=1),
     "config4": dict(n=250_000, k=30, B=4096, iters=1000, chains=0, max_iter=0, seed=4),
     "tiny": dict(n=5_000, k=30, B=256, iters=50, chains=2_000, max_iter=100, seed=9),
+    # config-2 shapes with few iterations: the command the ncu captures under profiles/ were taken on
+    "profile": dict(n=50_000, k=30, B=4096, iters=8, chains=20_000, max_iter=200, seed=2),
 }
 
 

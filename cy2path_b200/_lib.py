@@ -19,7 +19,8 @@ OK, ERR_INVALID_ARG, ERR_BAD_CSR, ERR_CDF_OVERSHOOT, ERR_CUDA, ERR_WORKSPACE, ER
 # every symbol the header declares (tests check the built library exports all of them)
 SYMBOLS = [
     "cy2p_abi_version", "cy2p_last_error", "cy2p_launch_count", "cy2p_plan_create", "cy2p_plan_create_host", "cy2p_plan_destroy",
-    "cy2p_plan_info", "cy2p_propagate_ws_bytes", "cy2p_propagate_column_tile", "cy2p_propagate", "cy2p_propagate_rows", "cy2p_cdf_build",
+    "cy2p_plan_info", "cy2p_propagate_ws_bytes", "cy2p_propagate_column_tile", "cy2p_propagate", "cy2p_propagate_rows",
+    "cy2p_propagate_f64_ws_bytes", "cy2p_propagate_f64", "cy2p_propagate_rows_f64", "cy2p_cdf_build",
     "cy2p_sample_chains", "cy2p_chain_history", "cy2p_fhmm_ws_bytes", "cy2p_fhmm_small_floats",
     "cy2p_fhmm_forward", "cy2p_fhmm_loss_grad",
 ]
@@ -54,6 +55,10 @@ def load():
     lib.cy2p_propagate_column_tile.argtypes = [_vp, _i32]
     lib.cy2p_propagate.argtypes = [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]
     lib.cy2p_propagate_rows.argtypes = [_vp, _vp, _vp, _i32, _i32, _i32, _vp]
+    lib.cy2p_propagate_f64_ws_bytes.argtypes = [_vp, _i32, _i32]
+    lib.cy2p_propagate_f64_ws_bytes.restype = _sz
+    lib.cy2p_propagate_f64.argtypes = lib.cy2p_propagate.argtypes
+    lib.cy2p_propagate_rows_f64.argtypes = lib.cy2p_propagate_rows.argtypes
     lib.cy2p_cdf_build.argtypes = [_vp, _vp, _vp, _i32, _vp]
     lib.cy2p_sample_chains.argtypes = [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]
     lib.cy2p_chain_history.argtypes = [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]
@@ -69,7 +74,8 @@ def load():
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and name not in ("cy2p_last_error", "cy2p_propagate_ws_bytes", "cy2p_fhmm_ws_bytes",
-                                           "cy2p_fhmm_small_floats", "cy2p_abi_version", "cy2p_launch_count"):
+                                           "cy2p_fhmm_small_floats", "cy2p_abi_version", "cy2p_launch_count",
+                                           "cy2p_propagate_f64_ws_bytes"):
             fn.restype = _i32
     _lib = lib
     return lib
@@ -144,12 +150,16 @@ class Plan:
 
 
 def propagate(plan, X0, iters, stationary=None, want_final=True, history_stride=0, want_eps=False):
-    """Run cy2p_propagate. X0: cuda float32 [n, B] (or [n]). Returns dict(final, history, eps) of cuda tensors."""
+    """Run cy2p_propagate (float32 X0) or cy2p_propagate_f64 (float64 X0). X0: cuda [n, B] (or [n]).
+    Returns dict(final, history, eps) of cuda tensors in X0's dtype (eps is always float64)."""
     torch = _torch()
     lib = load()
     squeeze = X0.dim() == 1
     X0 = X0.reshape(plan.n, -1).contiguous()
-    assert X0.dtype == torch.float32 and X0.is_cuda
+    assert X0.dtype in (torch.float32, torch.float64) and X0.is_cuda
+    f64 = X0.dtype == torch.float64
+    fn, ws_fn = (lib.cy2p_propagate_f64, lib.cy2p_propagate_f64_ws_bytes) if f64 else \
+        (lib.cy2p_propagate, lib.cy2p_propagate_ws_bytes)
     B = X0.shape[1]
     dev = X0.device
     with torch.cuda.device(dev):
@@ -161,12 +171,12 @@ def propagate(plan, X0, iters, stationary=None, want_final=True, history_stride=
         hist = None
         if history_stride:
             slots = (iters + history_stride - 1) // history_stride
-            hist = torch.empty((max(slots, 1), plan.n, B), dtype=torch.float32, device=dev)
+            hist = torch.empty((max(slots, 1), plan.n, B), dtype=X0.dtype, device=dev)
         eps = torch.empty((iters, B), dtype=torch.float64, device=dev) if want_eps else None
-        ws_bytes = lib.cy2p_propagate_ws_bytes(plan.handle, B, iters)
+        ws_bytes = ws_fn(plan.handle, B, iters)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(lib.cy2p_propagate(plan.handle, ptr(X0), B, iters, ptr(st), ptr(final), ptr(hist),
-                                 max(history_stride, 1), ptr(eps), ptr(ws), ws_bytes, stream_ptr(dev)))
+        check(fn(plan.handle, ptr(X0), B, iters, ptr(st), ptr(final), ptr(hist), max(history_stride, 1), ptr(eps),
+                 ptr(ws), ws_bytes, stream_ptr(dev)))
     if squeeze:
         final = final.reshape(-1) if final is not None else None
         hist = hist.reshape(hist.shape[0], plan.n) if hist is not None else None

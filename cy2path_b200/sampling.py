@@ -41,6 +41,12 @@ def get_plan(T, device=None):
     return plan
 
 
+def torch_dtype(precision):
+    import torch
+
+    return torch.float32 if precision == "fp32" else torch.float64
+
+
 def clear_plan_cache():
     _PLAN_CACHE.clear()
 
@@ -69,7 +75,9 @@ def batch_convergence(eps, tol, max_iter):
 
 def iterate_state_probability(adata, matrix_key="T_forward", init=None, stationary=None, max_iter=1000, tol=1e-5):
     """reference sampling.py:29-60. Returns (state_history, state_history_max_iter, convergence_check);
-    histories are float64 host arrays as in the reference (values are fp32-computed on the device)."""
+    histories are float64 host arrays as in the reference. The single-start case runs with a float64
+    iterate on the device (cy2p_propagate_f64): it is latency-bound, so float64 costs nothing, and the
+    history then tracks the reference's float64 arithmetic to ~1e-15 instead of drifting."""
     import torch
 
     T = adata.obsp[matrix_key]
@@ -77,13 +85,13 @@ def iterate_state_probability(adata, matrix_key="T_forward", init=None, stationa
     n = plan.n
     init64 = np.asarray(init, dtype=np.float64).reshape(n)
     dev = plan.device
-    x0 = torch.from_numpy(init64.astype(np.float32)).to(dev, non_blocking=True)
+    x0 = torch.from_numpy(np.ascontiguousarray(init64)).to(dev, non_blocking=True)
     out = _lib.propagate(plan, x0, int(max_iter), stationary=stationary, want_final=False, history_stride=1,
                          want_eps=True)
-    state_history_max_iter = np.empty((max_iter, n), dtype=np.float64)
     if max_iter > 0:
-        state_history_max_iter[:] = out["history"].cpu().numpy()
-        state_history_max_iter[0] = init64  # row 0 is the caller's start distribution verbatim (sampling.py:39)
+        state_history_max_iter = out["history"].cpu().numpy().reshape(max_iter, n)
+    else:
+        state_history_max_iter = np.empty((0, n), dtype=np.float64)
     eps_history = out["eps"].cpu().numpy() if max_iter > 0 else np.empty(0)
 
     convergence_check = check_convergence_criteria(eps_history, tol=tol)
@@ -96,20 +104,27 @@ def iterate_state_probability(adata, matrix_key="T_forward", init=None, stationa
     return state_history, state_history_max_iter, convergence_check
 
 
-def propagate_batch(adata_or_T, X0, iters, stationary=None, matrix_key="T_forward", tol=1e-5, return_device=False):
+def propagate_batch(adata_or_T, X0, iters, stationary=None, matrix_key="T_forward", tol=1e-5, return_device=False,
+                    precision="fp32"):
     """Batched form of the same simulation (BASELINE configs 2/4): B start distributions at once.
 
     X0: [n, B] float32 (numpy or cuda tensor), cell-major. Returns dict with ``final`` [n, B] and, when
     ``stationary`` is given, ``eps`` [iters, B] float64 and ``convergence`` [B] (the per-start cut of
-    reference sampling.py:48-57). The full [iters, n, B] history is not materialised (1.6 PB at config 2)."""
+    reference sampling.py:48-57). The full [iters, n, B] history is not materialised (1.6 PB at config 2).
+    ``precision``: "fp32" (default, the throughput path) or "fp64" (float64 iterate: tracks the reference's
+    float64 arithmetic over thousands of iterations at twice the memory traffic)."""
     import torch
+
+    if precision not in ("fp32", "fp64"):
+        raise ValueError("precision must be 'fp32' or 'fp64'")
+    tdt, ndt = (torch_dtype(precision), np.float32 if precision == "fp32" else np.float64)
 
     T = adata_or_T.obsp[matrix_key] if hasattr(adata_or_T, "obsp") else adata_or_T
     plan = get_plan(T)
     if torch.is_tensor(X0):
-        x0 = X0.to(plan.device, dtype=torch.float32)
+        x0 = X0.to(plan.device, dtype=tdt)
     else:
-        host = torch.from_numpy(np.ascontiguousarray(X0, dtype=np.float32))
+        host = torch.from_numpy(np.ascontiguousarray(X0, dtype=ndt))
         x0 = host.pin_memory().to(plan.device, non_blocking=True)
     out = _lib.propagate(plan, x0, int(iters), stationary=stationary, want_final=True, history_stride=0,
                          want_eps=stationary is not None)

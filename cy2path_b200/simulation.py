@@ -178,7 +178,7 @@ def _cluster_convergence(adata, column, stationary, state_indices, max_iter, tol
 
     cats = adata.obs[column].astype("category")
     by_cluster = pd.DataFrame({"cluster": cats, "probability": stationary}).groupby("cluster", observed=False).sum()
-    sequences = adata.obs[column].astype(str).values[state_indices]
+    sequences = np.asarray(adata.obs[column].astype(str), dtype=object)[state_indices]
     proportions = np.zeros((len(by_cluster), max_iter), dtype=np.float64)
     for r, cat in enumerate(by_cluster.index):
         proportions[r] = (sequences == str(cat)).mean(axis=0)

@@ -82,11 +82,23 @@ int32_t cy2p_propagate(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t it
                        const double *d_stationary, float *d_Xfinal, float *d_history,
                        int32_t history_stride, double *d_eps, void *d_ws, size_t ws_bytes, void *stream);
 
+/* float64 iterate: same contract with double X0 / Xfinal / history. Used for B == 1 — the reference's
+ * own case, whose history is float64 (sampling.py:33) — and for long batched runs: a float32 iterate
+ * cannot represent the ~1e-8 per-step growth that float32-rounded row sums give the reference's
+ * float64 iterate, so its relative L1 distance to the reference grows linearly with the iteration
+ * count (DESIGN.md "precision"). */
+size_t cy2p_propagate_f64_ws_bytes(const cy2p_plan *plan, int32_t B, int32_t iters);
+int32_t cy2p_propagate_f64(cy2p_plan *plan, const double *d_X0, int32_t B, int32_t iters,
+                           const double *d_stationary, double *d_Xfinal, double *d_history,
+                           int32_t history_stride, double *d_eps, void *d_ws, size_t ws_bytes, void *stream);
+
 /* Row-partitioned variant (BASELINE config 5): computes only destination rows [row_begin,row_end)
  * of one update, Y[row_begin:row_end, :] = (X . T)[row_begin:row_end, :], reading the whole X.
  * The caller (cy2path_b200/dist.py) all-gathers the slices between iterations. */
 int32_t cy2p_propagate_rows(cy2p_plan *plan, const float *d_X, float *d_Y, int32_t B,
                             int32_t row_begin, int32_t row_end, void *stream);
+int32_t cy2p_propagate_rows_f64(cy2p_plan *plan, const double *d_X, double *d_Y, int32_t B,
+                                int32_t row_begin, int32_t row_end, void *stream);
 
 /* ---- K0/K2: chain sampling ------------------------------------------------------------------
  * cy2p_cdf_build replaces extract_nonzero_entries (simulation.py:15-53): idx int32 [n][W] and

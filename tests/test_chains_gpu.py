@@ -117,7 +117,7 @@ def test_duplicate_and_unsorted_columns():
     idx, cum = c2p.extract_nonzero_entries(ad)
     ridx, rcum = ochains.extract_nonzero_entries(T)
     assert np.array_equal(idx, ridx) and np.array_equal(cum, rcum)
-    uni = np.array([[0.6, 0.1, 0.9, 0.3]])  # from state 0: r=0.6 -> third entry (col 2, duplicate)
+    uni = np.array([[0.6, 0.1, 0.6, 0.3]])  # from state 0: r=0.6 -> third entry (col 2, duplicate)
     s, p = c2p.iterate_markov_chain(ad, max_iter=5, init_state=0, uniforms=uni[0])
     rs, rp = ochains.sample_chains(T, idx, cum, np.array([0]), uni)
     assert np.array_equal(s, rs[0]) and np.array_equal(p, rp[0])

@@ -1,0 +1,77 @@
+"""CPU tests of the multi-GPU layer's host logic with world_size-2 gloo process groups.
+
+The per-rank arithmetic of the product is CUDA; here the row update is supplied by the oracle so that
+the sharding and the per-iteration all-gather exchange can be checked against the unsharded result.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cy2path_b200 import dist as c2dist
+
+
+def test_shard_range_covers_everything():
+    for total in (0, 1, 7, 4096, 100_001):
+        for world in (1, 2, 3, 8):
+            spans = [c2dist.shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_row_blocks():
+    m, blocks = c2dist.row_blocks(10, 4)
+    assert m == 3 and blocks == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    m, blocks = c2dist.row_blocks(5, 8)
+    assert m == 1 and blocks[5:] == [(5, 5)] * 3
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.sparse as sp
+
+        from cy2path_b200.synth import batched_starts, knn_velocity_tpm
+
+        g = knn_velocity_tpm(301, k=6, seed=17)
+        T = g["T"]
+        Tt = sp.csr_matrix(T.T.astype(np.float64))
+        X0 = torch.from_numpy(batched_starts(T, 5, seed=1).astype(np.float64))
+
+        def update(X, Y, r0, r1):  # oracle arithmetic for rows [r0, r1): y[j,:] = sum_i T[i,j] x[i,:]
+            Y[r0:r1] = torch.from_numpy(Tt[r0:r1] @ X[:T.shape[0]].numpy())
+
+        out = c2dist.propagate_row_partitioned(T.shape[0], X0, 9, update)
+        ref = X0.numpy().copy()
+        for _ in range(9):
+            ref = Tt @ ref
+        assert np.abs(out.numpy() - ref).max() <= 1e-14
+        # ragged gather of per-start results (batch sharding's only exchange)
+        b, e = c2dist.shard_range(11, world, rank)
+        allv = c2dist.gather_ragged_int64(np.arange(b, e), None)
+        assert np.array_equal(allv, np.arange(11))
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_row_partition_and_gather_world2_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()

@@ -1,0 +1,139 @@
+"""GPU parity tests for K3 (FHMM forward, loss terms, analytic gradients, trainer) vs reference golden + oracle.
+
+Parity bar: forward outputs and loss terms within 1e-5 max-abs; log-likelihood within 1e-6 relative
+(its magnitude ~ I*log N is beyond fp32's 1e-5 absolute resolution); gradients
+within 1e-5 + 1e-3*max|g| of the reference's autograd.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fhmm as ofhmm
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ("unnormalized_state_init", "unnormalized_chain_weights", "unnormalized_emission_matrix",
+         "unnormalized_transition_matrix")
+
+
+def _model_from(g):
+    from cy2path_b200.models import FHMM
+
+    m = FHMM(int(g["S"]), int(g["L"]), int(g["N"]), int(g["I"]), restricted=bool(g["restricted"]), use_gpu=True)
+    m.load_state_dict({k: torch.tensor(g[k]) for k in NAMES})
+    return m
+
+
+@pytest.mark.parametrize("name", ["fhmm_restricted.npz", "fhmm_unrestricted.npz", "fhmm_single_chain.npz"])
+def test_forward_matches_reference_golden(golden, name):
+    g = golden(name)
+    m = _model_from(g)
+    pred, joint, hidden = m.forward_model()
+    assert pred.shape == g["pred"].shape and joint.shape == g["joint"].shape and hidden.shape == g["hidden"].shape
+    assert np.abs(pred.cpu().numpy() - g["pred"]).max() <= 1e-5
+    assert np.abs(hidden.cpu().numpy() - g["hidden"]).max() <= 1e-5
+    assert np.abs(joint.cpu().numpy() - g["joint"]).max() <= 1e-5
+    # attributes other code reads (infer_dynamics.py:56-64)
+    assert m.log_emission_matrix.shape == g["unnormalized_emission_matrix"].shape
+    assert m.log_transition_matrix.shape == (int(g["S"]), int(g["S"]))
+    assert m.log_transition_matrix_.shape == g["unnormalized_transition_matrix"].shape
+
+
+@pytest.mark.parametrize("name", ["fhmm_restricted.npz", "fhmm_unrestricted.npz", "fhmm_single_chain.npz"])
+def test_loss_terms_and_gradients_match_reference_golden(golden, name):
+    from cy2path_b200 import _lib
+    from cy2path_b200.sampling import get_plan
+
+    g = golden(name)
+    m = _model_from(g)
+    plan = get_plan(g["T"])
+    D = torch.tensor(g["D"]).cuda()
+    terms, grads, _ = _lib.fhmm_loss_grad(plan, *[p.data for p in m.parameters()], D, bool(g["restricted"]),
+                                          tuple(g["weights"]))
+    t = dict(zip(_lib.TERM_NAMES, terms.cpu().numpy().tolist()))
+    ref = dict(zip(g["term_names"].tolist(), g["term_values"].tolist()))
+    for k in ("loss", "divergence", "sparsity", "orthogonality", "regularisation"):
+        assert abs(t[k] - ref[k]) <= 1e-5 + 1e-5 * abs(ref[k]), (k, t[k], ref[k])
+    if int(g["L"]) > 1:
+        assert abs(t["exclusivity"] - ref["exclusivity"]) <= 1e-5
+    assert abs(t["log_likelihood"] - ref["likelihood"]) <= 1e-6 * abs(ref["likelihood"]) + 1e-5
+    for gq, nme in zip(grads, NAMES):
+        rg = g["grad_" + nme]
+        assert gq.shape == rg.shape
+        assert np.abs(gq.cpu().numpy() - rg).max() <= 1e-5 + 1e-3 * np.abs(rg).max(), nme
+
+
+@pytest.mark.parametrize("S,L,restricted,N,I", [(10, 4, True, 2000, 60), (5, 3, False, 1500, 40), (12, 2, True, 777, 33),
+                                                 (3, 1, False, 300, 9)])
+def test_mid_size_vs_oracle_autograd(S, L, restricted, N, I):
+    import scipy.sparse as sp
+
+    from cy2path_b200 import _lib
+    from cy2path_b200.models import FHMM
+    from cy2path_b200.sampling import get_plan
+    from cy2path_b200.synth import knn_velocity_tpm
+
+    g = knn_velocity_tpm(N, k=12, seed=31)
+    T = g["T"]
+    plan = get_plan(T)
+    x0 = torch.tensor((g["root_cells"] / g["root_cells"].sum()).astype(np.float32)).cuda()
+    D = _lib.propagate(plan, x0, I, history_stride=1, want_final=False)["history"].contiguous()
+    torch.manual_seed(7)
+    m = FHMM(S, L, N, I, restricted=restricted, use_gpu=True)
+    wts = (1.0, 0.1, 0.1, 0.05)
+    terms, grads, _ = _lib.fhmm_loss_grad(plan, *[p.data for p in m.parameters()], D, restricted, wts)
+    th = [p.detach().cpu().clone().requires_grad_(True) for p in m.parameters()]
+    coo = sp.coo_matrix(T)
+    Tt = torch.sparse_coo_tensor(np.vstack([coo.row, coo.col]), coo.data.astype(np.float32), (N, N)).coalesce()
+    ref = ofhmm.loss_terms(*th, D.cpu(), Tt, weights=wts)
+    ref["loss"].backward()
+    t = dict(zip(_lib.TERM_NAMES, terms.cpu().numpy().tolist()))
+    for k in ("loss", "divergence", "sparsity", "orthogonality", "regularisation"):
+        assert abs(t[k] - ref[k].item()) <= 2e-5 + 2e-5 * abs(ref[k].item()), (k, t[k], ref[k].item())
+    if L > 1:
+        assert abs(t["exclusivity"] - ref["exclusivity"].item()) <= 2e-5
+    ll = ref["log_likelihood"].item()
+    assert abs(t["log_likelihood"] - ll) <= 2e-6 * abs(ll) + 1e-5
+    for gq, r, nme in zip(grads, th, NAMES):
+        rg = r.grad.numpy()
+        assert np.abs(gq.cpu().numpy() - rg).max() <= 1e-5 + 2e-3 * np.abs(rg).max(), nme
+    pred = m.forward_model(want_joint=False)[0]
+    assert np.abs(pred.cpu().numpy() - ref["pred"].detach().numpy()).max() <= 2e-5
+
+
+def test_trainer_drop_in(golden):
+    g = golden("fhmm_restricted.npz")
+    m = _model_from(g)
+    D = torch.tensor(g["D"])
+    m.train(D, TPM=g["T"], num_epochs=3)  # default weights, default RMSprop(lr=0.2)
+    assert m.elapsed_epochs == 3 and len(m.loss_values) == 3 and len(m.exclusivity_values) == 3
+    traj = g["traj"]  # rows: loss, div, likelihood, sparsity, orth, excl, reg (reference, 3 epochs)
+    assert abs(m.loss_values[0] - traj[0, 0]) <= 1e-5 * max(1, abs(traj[0, 0]))
+    assert abs(m.divergence_values[0] - traj[1, 0]) <= 1e-5
+    assert abs(m.likelihood_values[0] - traj[2, 0]) <= 1e-6 * abs(traj[2, 0]) + 1e-5
+    # RMSprop's first step is lr*sign(g): entries with |g| ~ rounding noise may step the other way, so later
+    # epochs are compared loosely
+    assert np.allclose(m.loss_values, traj[0], rtol=5e-2)
+    assert isinstance(m.avg_corrcoeff, float) and -1 <= m.avg_corrcoeff <= 1
+    assert float(m.log_likelihood) == pytest.approx(m.likelihood_values[-1])
+    # resume keeps history (infer_joint_dynamics relies on it, trainer.py:76-114)
+    m.train(D, TPM=g["T"], num_epochs=2)
+    assert m.elapsed_epochs == 5 and len(m.loss_values) == 5
+    assert m.loss_values[-1] < m.loss_values[0]
+
+
+def test_training_reduces_loss_at_moderate_size():
+    from cy2path_b200 import _lib
+    from cy2path_b200.models import FHMM
+    from cy2path_b200.sampling import get_plan
+    from cy2path_b200.synth import knn_velocity_tpm
+
+    g = knn_velocity_tpm(3000, k=15, seed=3)
+    plan = get_plan(g["T"])
+    x0 = torch.tensor((g["root_cells"] / g["root_cells"].sum()).astype(np.float32)).cuda()
+    D = _lib.propagate(plan, x0, 80, history_stride=1, want_final=False)["history"].contiguous()
+    torch.manual_seed(3)
+    m = FHMM(10, 4, 3000, 80, restricted=True, use_gpu=True)
+    m.train(D, TPM=g["T"], num_epochs=60)
+    assert np.isfinite(m.loss_values).all()
+    assert m.loss_values[-1] < 0.7 * m.loss_values[0]

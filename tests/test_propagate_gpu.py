@@ -47,6 +47,8 @@ def test_history_matches_reference_golden(golden, name):
     for i in range(shm.shape[0]):
         _assert_close(shm[i], g["history"][i])
     assert np.array_equal(shm[0], g["init"])
+    # the single-start path iterates in float64 on the device: far inside the bar
+    assert np.abs(shm - g["history"]).max() <= 1e-12
 
 
 def test_config1_shape_full_history_vs_oracle():
@@ -64,8 +66,10 @@ def test_config1_shape_full_history_vs_oracle():
     assert np.abs(hist - ref_hist).max() <= MAX_ABS
     worst = max(omsm.rel_l1(hist[i], ref_hist[i]) for i in range(0, 1000, 7))
     assert worst <= REL_L1
-    # mass conservation / non-negativity (size-independent properties)
-    assert np.abs(hist.sum(1) - 1).max() <= 1e-5 and hist.min() >= 0
+    # the float64 single-start path tracks the reference far inside the bar, including the slow growth of the
+    # total mass (float32-rounded rows of T do not sum to exactly 1; the reference's float64 state keeps that)
+    assert np.abs(hist - ref_hist).max() <= 1e-12
+    assert np.abs(hist.sum(1) - ref_hist.sum(1)).max() <= 1e-12 and hist.min() >= 0
 
 
 @pytest.mark.parametrize("B,iters", [(1, 5), (3, 4), (4, 6), (32, 9), (128, 7), (132, 5), (384, 3)])
@@ -97,6 +101,32 @@ def test_batched_matches_oracle_and_equals_looped(B, iters):
         for b in range(B):
             one = _lib.propagate(plan, torch.from_numpy(np.ascontiguousarray(X0[:, b])).cuda(), iters)
             assert np.abs(one["final"].cpu().numpy() - got[:, b]).max() <= 1e-7
+
+
+def test_long_run_precision_fp32_vs_fp64_iterate():
+    """1,000 iterations, 8 starts on the config-1 graph. A float32 iterate cannot follow the reference's float64
+    iterate to 1e-6 relative L1 over this many steps (the float32-rounded rows of T sum to 1 +- 1e-8 and the
+    reference's float64 state accumulates that growth, which float32 storage rounds away): it is held to the
+    max-abs bar and to a stated 1e-4 relative L1; the float64 iterate is held to the full north_star bar."""
+    import torch
+
+    from cy2path_b200.sampling import propagate_batch
+    from cy2path_b200.synth import batched_starts, knn_velocity_tpm
+
+    g = knn_velocity_tpm(3696, k=30, seed=1)
+    T = g["T"]
+    X0 = batched_starts(T, 8, seed=4)
+    ref = ofast.propagate_batch(T, X0, 1000)
+    r32 = propagate_batch(T, X0, 1000)["final"]
+    r64 = propagate_batch(T, X0, 1000, precision="fp64")["final"]
+    assert r32.dtype == np.float32 and r64.dtype == np.float64
+    assert np.abs(r64 - ref).max() <= 1e-12 and omsm.rel_l1(r64, ref) <= 1e-12
+    assert np.abs(r32 - ref).max() <= MAX_ABS
+    assert omsm.rel_l1(r32, ref) <= 1e-4
+    # short horizons: the float32 iterate meets the full bar
+    ref60 = ofast.propagate_batch(T, X0, 60)
+    r32s = propagate_batch(T, X0, 60)["final"]
+    _assert_close(r32s, ref60)
 
 
 def test_history_stride_and_linearity():
@@ -146,7 +176,10 @@ def test_row_partition_equals_full_update():
         for r0, r1 in zip(bounds[:-1], bounds[1:]):
             _lib.check(_lib.load().cy2p_propagate_rows(plan.handle, _lib.ptr(X), _lib.ptr(Y), B, r0, r1,
                                                        _lib.stream_ptr()))
-        assert torch.equal(Y, full)
+        if B == 1:  # B == 1 full update uses the lane-parallel row sum: same values up to fp32 rounding
+            assert torch.allclose(Y, full, rtol=0, atol=1e-7)
+        else:
+            assert torch.equal(Y, full)
 
 
 def test_bad_csr_and_workspace_errors():
