@@ -110,6 +110,30 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+def to_device(a, dtype, dev):
+    """Host array (numpy) or tensor -> contiguous device tensor of `dtype`. Pinned host memory is copied
+    asynchronously at PCIe speed; pageable memory goes through the driver's staging copy (no extra pinning pass)."""
+    torch = _torch()
+    if torch.is_tensor(a):
+        return a.to(dev, dtype=dtype).contiguous()
+    host = torch.from_numpy(np.ascontiguousarray(a))
+    if host.dtype != dtype and not host.is_pinned():
+        host = host.to(dtype)  # convert on the host once rather than moving the wider type
+    return host.to(dev, non_blocking=host.is_pinned()).to(dtype).contiguous()
+
+
+def to_host(t):
+    """Device tensor -> numpy array backed by pinned host memory (torch caches the pinned blocks, so repeated
+    calls copy at PCIe speed instead of through a pageable staging buffer)."""
+    torch = _torch()
+    if t.numel() * t.element_size() < (1 << 20):
+        return t.cpu().numpy()
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return out.numpy()
+
+
 class Plan:
     """Device-resident T and T^T for one transition matrix on one device (cy2p_plan)."""
 

@@ -89,7 +89,7 @@ def iterate_state_probability(adata, matrix_key="T_forward", init=None, stationa
     out = _lib.propagate(plan, x0, int(max_iter), stationary=stationary, want_final=False, history_stride=1,
                          want_eps=True)
     if max_iter > 0:
-        state_history_max_iter = out["history"].cpu().numpy().reshape(max_iter, n)
+        state_history_max_iter = _lib.to_host(out["history"]).reshape(max_iter, n)
     else:
         state_history_max_iter = np.empty((0, n), dtype=np.float64)
     eps_history = out["eps"].cpu().numpy() if max_iter > 0 else np.empty(0)
@@ -117,20 +117,16 @@ def propagate_batch(adata_or_T, X0, iters, stationary=None, matrix_key="T_forwar
 
     if precision not in ("fp32", "fp64"):
         raise ValueError("precision must be 'fp32' or 'fp64'")
-    tdt, ndt = (torch_dtype(precision), np.float32 if precision == "fp32" else np.float64)
+    tdt = torch_dtype(precision)
 
     T = adata_or_T.obsp[matrix_key] if hasattr(adata_or_T, "obsp") else adata_or_T
     plan = get_plan(T)
-    if torch.is_tensor(X0):
-        x0 = X0.to(plan.device, dtype=tdt)
-    else:
-        host = torch.from_numpy(np.ascontiguousarray(X0, dtype=ndt))
-        x0 = host.pin_memory().to(plan.device, non_blocking=True)
+    x0 = _lib.to_device(X0, tdt, plan.device)
     out = _lib.propagate(plan, x0, int(iters), stationary=stationary, want_final=True, history_stride=0,
                          want_eps=stationary is not None)
-    res = {"final": out["final"] if return_device else out["final"].cpu().numpy()}
+    res = {"final": out["final"] if return_device else _lib.to_host(out["final"])}
     if out["eps"] is not None:
-        eps = out["eps"].cpu().numpy()
+        eps = _lib.to_host(out["eps"])
         res["eps"] = eps
         conv = batch_convergence(eps, tol, iters)
         res["convergence"] = conv

@@ -49,12 +49,7 @@ def _walk(plan, idx_d, cum_d, init_states, uniforms, want_history_steps=None):
     dev = plan.device
 
     def to_dev(a, dtype):
-        if torch.is_tensor(a):
-            return a.to(dev, dtype=dtype).contiguous()
-        host = torch.from_numpy(np.ascontiguousarray(a))
-        if host.numel() * host.element_size() > (1 << 20):
-            host = host.pin_memory()
-        return host.to(dev, non_blocking=True).to(dtype).contiguous()
+        return _lib.to_device(a, dtype, dev)
 
     with torch.cuda.device(dev):
         init_d = to_dev(init_states, torch.int32).reshape(-1)
@@ -121,9 +116,9 @@ def sample_markov_chains(data, matrix_key="T_forward", recalc_matrix=False, self
         uniforms = np.random.rand(num_chains, max_iter - 1)
     states_d, probs_d, hist_d = _walk(plan, idx_d, cum_d, np.asarray(init_states, dtype=np.int32), uniforms,
                                       want_history_steps=max_iter)
-    state_indices = states_d.cpu().numpy()
-    state_transition_probabilities = probs_d.cpu().numpy()
-    state_history_max_iter = hist_d.cpu().numpy()  # unvisited entries are 0 (np.empty in the reference)
+    state_indices = _lib.to_host(states_d)
+    state_transition_probabilities = _lib.to_host(probs_d)
+    state_history_max_iter = _lib.to_host(hist_d)  # unvisited entries are 0 (np.empty in the reference)
 
     cluster_out = None
     if isinstance(convergence, str) and convergence == "auto":

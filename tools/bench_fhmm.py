@@ -1,0 +1,100 @@
+"""BASELINE config 3: FHMM training, S=10, L=4, N=50,000 cells, I=500 history rows (tuning/measurement aid).
+
+Reports epochs/s of the CUDA path (cy2p_fhmm_loss_grad + torch RMSprop step) and, at a reduced shape
+that fits, the oracle's eager-torch restatement of the reference's epoch on the same GPU and on the CPU.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--N", type=int, default=50000)
+    ap.add_argument("--I", type=int, default=500)
+    ap.add_argument("--S", type=int, default=10)
+    ap.add_argument("--L", type=int, default=4)
+    ap.add_argument("--epochs", type=int, default=100)
+    ap.add_argument("--unrestricted", action="store_true")
+    ap.add_argument("--oracle", action="store_true", help="also time the oracle's eager torch epoch (GPU + CPU)")
+    a = ap.parse_args()
+    import torch
+
+    from cy2path_b200 import _lib
+    from cy2path_b200.models import FHMM
+    from cy2path_b200.sampling import get_plan
+    from cy2path_b200.synth import knn_velocity_tpm
+
+    g = knn_velocity_tpm(a.N, seed=3)
+    T = g["T"]
+    plan = get_plan(T)
+    x0 = torch.tensor((g["root_cells"] / g["root_cells"].sum()).astype(np.float32)).cuda()
+    D = _lib.propagate(plan, x0, a.I, history_stride=1, want_final=False)["history"].contiguous()
+    torch.manual_seed(3)
+    m = FHMM(a.S, a.L, a.N, a.I, restricted=not a.unrestricted, use_gpu=True)
+    m.train(D, TPM=T, num_epochs=5)
+    torch.cuda.synchronize()
+    # kernel-only: loss+grad calls
+    params = [p.data for p in m.parameters()]
+    w = (1.0, 0.1, 0.1, 0.0)
+    _, _, bufs = _lib.fhmm_loss_grad(plan, *params, D, not a.unrestricted, w)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        _lib.fhmm_loss_grad(plan, *params, D, not a.unrestricted, w, out=bufs)
+    e1.record()
+    torch.cuda.synchronize()
+    lg_ms = e0.elapsed_time(e1) / 50
+    t0 = time.perf_counter()
+    m.train(D, TPM=T, num_epochs=a.epochs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {"N": a.N, "I": a.I, "S": a.S, "L": a.L, "restricted": not a.unrestricted,
+           "loss_grad_ms": lg_ms, "epoch_ms_train_loop": dt / a.epochs * 1e3, "epochs_per_s": a.epochs / dt,
+           "cell_iters_per_s": a.N * a.I * a.epochs / dt, "loss_first": m.loss_values[0], "loss_last": m.loss_values[-1],
+           "D_bytes": a.N * a.I * 4, "D_pass_GBps": a.N * a.I * 4 / (lg_ms * 1e-3) / 1e9}
+    if a.oracle:
+        from oracle import fhmm as ofhmm
+        import scipy.sparse as sp
+
+        Nr, Ir = min(a.N, 3696), min(a.I, 430)
+        gr = knn_velocity_tpm(Nr, seed=3)
+        coo = sp.coo_matrix(gr["T"])
+        for dev in ("cuda", "cpu"):
+            Tt = torch.sparse_coo_tensor(np.vstack([coo.row, coo.col]), coo.data.astype(np.float32), (Nr, Nr)).coalesce().to(dev)
+            Dr = torch.rand(Ir, Nr, device=dev)
+            Dr /= Dr.sum(1, keepdim=True)
+            torch.manual_seed(3)
+            th = [torch.randn(a.S, a.L, device=dev, requires_grad=True), torch.randn(a.L, device=dev, requires_grad=True),
+                  torch.randn(a.S, 1, Nr, device=dev, requires_grad=True), torch.randn(a.L, a.S, a.S, device=dev, requires_grad=True)]
+            ones = {"S": torch.ones(a.S, device=dev), "L": torch.ones(a.L, device=dev)}
+            reps = 3
+            if dev == "cuda":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                for p in th:
+                    p.grad = None
+                o = ofhmm.loss_terms(*th, Dr, Tt, weights=(1.0, 0.1, 0.1, 0.0)) if dev == "cpu" else None
+                if o is None:
+                    # oracle.loss_terms builds CPU ones(); on cuda run the same graph via forward_model + KL only
+                    pred, joint, hidden, _ = ofhmm.forward_model(*th, Ir)
+                    loss = torch.nn.functional.kl_div(pred, Dr, reduction="batchmean")
+                else:
+                    loss = o["loss"]
+                loss.backward()
+            if dev == "cuda":
+                torch.cuda.synchronize()
+            out[f"oracle_epoch_ms_{dev}_N{Nr}_I{Ir}"] = (time.perf_counter() - t0) / reps * 1e3
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
