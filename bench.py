@@ -49,7 +49,7 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------ inputs
-def make_inputs(w, rank):
+def make_inputs(w, rank, with_chains=True):
     from cy2path_b200.synth import batched_starts, chain_inputs, knn_velocity_tpm, stationary_by_power
 
     g = knn_velocity_tpm(w["n"], k=w["k"], seed=w["seed"])
@@ -58,7 +58,7 @@ def make_inputs(w, rank):
     X0 = batched_starts(T, w["B"], seed=w["seed"] + 1000 * rank)
     root = g["root_cells"] / g["root_cells"].sum()
     init_s = uni = None
-    if w["chains"]:
+    if w["chains"] and with_chains:
         init_s, uni = chain_inputs(T, root, w["chains"], w["max_iter"], seed=w["seed"] + 1000 * rank)
     return dict(T=T, stat=stat, X0=X0, root=root, end=g["end_points"], root_cells=g["root_cells"], init_s=init_s,
                 uni=uni)
@@ -111,15 +111,17 @@ def _cpu_worker(args):
     sampling.py:38-45) on a slice of the start distributions."""
     indptr, indices, data, n, Xs, stat, iters = args
     import scipy.sparse as sp
+    from threadpoolctl import threadpool_limits
 
     from oracle import msm as omsm
 
     T = sp.csr_matrix((data, indices, indptr), shape=(n, n))
     X = np.asarray(Xs, dtype=np.float64)  # [b, n]
-    for _ in range(iters):
-        X = np.asarray(X @ T)
-        for b in range(X.shape[0]):
-            omsm.cosine_distance(X[b], stat)
+    with threadpool_limits(1):  # one BLAS thread per worker process: the workers are the parallelism
+        for _ in range(iters):
+            X = np.asarray(X @ T)
+            for b in range(X.shape[0]):
+                omsm.cosine_distance(X[b], stat)
     return float(X.sum())
 
 
@@ -168,7 +170,7 @@ def run_reference(args, w):
         return
     import multiprocessing as mp
 
-    inp = make_inputs(w, 0)
+    inp = make_inputs(w, 0, with_chains=False)
     cores = max(1, min(os.cpu_count() or 1, 64))
     b_per_core, iters = 8, 25  # bounded sample per step: cores*8 starts x 25 iterations
     pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
@@ -227,7 +229,10 @@ def run_b200(args, w):
     T, n, B, iters = inp["T"], w["n"], w["B"], w["iters"]
     dev = torch.device("cuda", local)
     plan = get_plan(T)
+    single = B == 1
     X0_d = torch.from_numpy(inp["X0"]).to(dev)
+    if single:
+        X0_d = X0_d.double().reshape(-1)
     stat_d = torch.from_numpy(inp["stat"]).to(dev)
     has_chains = bool(w["chains"])
     if has_chains:
@@ -242,7 +247,10 @@ def run_b200(args, w):
     def step_device():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = _lib.propagate(plan, X0_d, iters, stationary=stat_d, want_final=True, want_eps=True)
+        if single:  # sampling.iterate_state_probability: float64 iterate, every iterate kept
+            out = _lib.propagate(plan, X0_d, iters, stationary=stat_d, want_final=False, history_stride=1, want_eps=True)
+        else:
+            out = _lib.propagate(plan, X0_d, iters, stationary=stat_d, want_final=True, want_eps=True)
         e1.record()
         prop_ms.append((e0, e1))
         if has_chains:
@@ -281,8 +289,12 @@ def run_b200(args, w):
     # ---- roofline of the dominant kernel (spmm_gather): algorithmic bytes per launch / mean launch duration
     tile = int(lib.cy2p_propagate_column_tile(plan.handle, B))
     tiles = (B + tile - 1) // tile
-    gather_launches = tiles * iters
-    bytes_per_launch = 8 * T.nnz + 4 * (n + 1) + 2 * 4 * n * min(tile, B)  # 8 nnz + 4(n+1) + 8 n b
+    if single:  # one cooperative launch runs all iterations (float64 iterate: 8-byte elements)
+        gather_launches = 1
+        bytes_per_launch = iters * (8 * T.nnz + 4 * (n + 1) + 2 * 8 * n)
+    else:
+        gather_launches = tiles * iters
+        bytes_per_launch = 8 * T.nnz + 4 * (n + 1) + 2 * 4 * n * min(tile, B)  # 8 nnz + 4(n+1) + 8 n b
     launch_s = prop_ms_avg * 1e-3 / gather_launches
     peaks = {}
     try:
@@ -292,8 +304,13 @@ def run_b200(args, w):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bytes_per_launch / launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "spmm_gather<4,true>", "bytes_per_launch": bytes_per_launch,
+                "traffic": None, "kernel": "spmv_b1_persistent<double>" if single else "spmm_gather<float,4,true>",
+                "bytes_per_launch": bytes_per_launch,
                 "launch_us": launch_s * 1e6, "launches_per_step": gather_launches, "column_tile": tile,
+                # the resource that actually binds K1: every product needs its own gathered operand,
+                # nnz x columns x 4 B per update flow L2 -> SM (64 B/clk/SM fill path = 18.2 TB/s at 1.92 GHz)
+                "l2_gather_TBps": (None if single else T.nnz * min(tile, B) * 4 / launch_s / 1e12),
+                "l2_fill_peak_TBps": 148 * 64 * 1.92e9 / 1e12,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (sustained copy)" if peaks else "fallback 6650 GB/s"}
 
     # ---- end to end through the public API with host buffers (H2D of T, X0, uniforms; D2H of results)
@@ -308,7 +325,13 @@ def run_b200(args, w):
             from cy2path_b200.sampling import clear_plan_cache
 
             clear_plan_cache()  # the plan (H2D of T, transpose, tables) is rebuilt inside the timed step
-            r = c2p.propagate_batch(T, inp["X0"], iters, stationary=inp["stat"])
+            if single:
+                ad0 = Adata()
+                ad0.obsp, ad0.shape, ad0.uns = {"T_forward": T}, (n, 0), {}
+                r = c2p.iterate_state_probability(ad0, init=inp["X0"][:, 0].astype(np.float64), stationary=inp["stat"],
+                                                  max_iter=iters)
+            else:
+                r = c2p.propagate_batch(T, inp["X0"], iters, stationary=inp["stat"])
             if has_chains:
                 ad = Adata()
                 ad.obsp, ad.shape, ad.uns = {"T_forward": T}, (n, 0), {}
@@ -333,8 +356,8 @@ def run_b200(args, w):
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        h2d = T.nnz * 8 + 4 * (n + 1) + n * B * 4 + n * 8
-        d2h = n * B * 4 + iters * B * 8
+        h2d = T.nnz * 8 + 4 * (n + 1) + n * B * (8 if single else 4) + n * 8
+        d2h = (iters * n * 8 if single else n * B * 4) + iters * B * 8
         if has_chains:
             h2d += w["chains"] * (w["max_iter"] - 1) * 8 + w["chains"] * 4
             d2h += w["chains"] * w["max_iter"] * 4 + w["chains"] * (w["max_iter"] - 1) * 4 + w["max_iter"] * n * 4
@@ -345,7 +368,8 @@ def run_b200(args, w):
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb, ci = min(32, B), max(1, int(1.2e9 / (n * min(32, B))))  # ~1.2e9 cell-iterations: 10-30 s of one core
+        cb = min(32, B)
+        ci = max(1, min(int(1.2e9 / (n * cb)), 20 * iters))  # ~1.2e9 cell-iterations: 10-30 s of one core
         rate, secs = cpu_reference_rate(inp, w, 1, cb, ci)
         cpu = {"value": rate, "unit": "cell-iterations/s", "cores": 1, "kind": "port",
                "sample": f"1 thread, {cb} starts x {ci} iterations of scipy x@T + cosine ({secs:.1f} s)",
@@ -358,7 +382,7 @@ def run_b200(args, w):
         line = {
             "metric": "msm_cell_iterations_per_s", "value": value, "unit": "cell-iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if single else "f32", "data": "synthetic",
             "config": workload_config(w, args, world), "clocks": clocks.summary(), "gpu_launches": int(launches),
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
             "detail": {"propagate_ms_per_step": prop_ms_avg, "chains_ms_per_step": chain_ms,

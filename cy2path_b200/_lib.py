@@ -213,7 +213,7 @@ def _fhmm_ws(S, L, N, I, dev):
     torch = _torch()
     nbytes = load().cy2p_fhmm_ws_bytes(S, L, N, I)
     if nbytes == 0:
-        raise ValueError("unsupported model size (supported: S <= 64, L <= 16, S*L <= 256)")
+        raise ValueError("unsupported model size (supported: S <= 32, L <= 16, S*(1 if restricted else L) <= 64)")
     return torch.empty(nbytes, dtype=torch.uint8, device=dev), nbytes
 
 

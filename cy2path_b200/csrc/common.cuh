@@ -50,6 +50,7 @@ struct cy2p_plan {
     int32_t device = 0;
     int32_t num_sms = 0;
     int32_t max_in_deg = 0, max_out_deg = 0, W = 0;
+    bool canonical_rows = false;  // every row of T has strictly increasing column indices (no duplicates)
     size_t bytes_owned = 0;
     size_t l2_bytes = 0;
     // T as given (CSR, device copies owned by the plan)

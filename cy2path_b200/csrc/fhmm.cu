@@ -19,7 +19,7 @@
 
 namespace cy2p {
 
-constexpr int kMaxS = 64, kMaxL = 16, kMaxK = 64;
+constexpr int kMaxS = 32, kMaxL = 16, kMaxK = 64;  // one warp per lineage, lane = latent state
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -38,51 +38,78 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // --------------------------------------------------------------------------------------------------
-// log_softmax over the N nodes of every emission row (methods.py:17-19). One CTA per row.
-// row_lse[row] (double) = logsumexp of the written row (the ~1e-7 residual the reference's
-// compute_log_likelihood subtracts, methods.py:33-34).
-__global__ void __launch_bounds__(1024) emission_logsoftmax(int N, const float *__restrict__ theta,
-                                                            float *__restrict__ logE, double *__restrict__ row_lse) {
-    const float *x = theta + (size_t)blockIdx.x * N;
-    float *y = logE + (size_t)blockIdx.x * N;
-    __shared__ float smax[32];
-    __shared__ double ssum[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+// log_softmax over the N nodes of every emission row (methods.py:17-19), two launches, grid (row, chunk):
+//   pass 1: per-chunk (max, sum exp(x - max)) partials;  pass 2: combine the row's partials, write
+//   logE = x - lse and accumulate row_sum[row] += sum exp(logE) in float64 (log of it is the ~1e-7 residual the
+//   reference's compute_log_likelihood subtracts, methods.py:33-34).
+constexpr int kSoftmaxChunk = 4096;
+
+__global__ void __launch_bounds__(256) emission_softmax_partials(int N, const float *__restrict__ theta,
+                                                                 float2 *__restrict__ partials) {
+    const int row = blockIdx.x, chunk = blockIdx.y, nchunks = gridDim.y;
+    const float *x = theta + (size_t)row * N;
+    const int i0 = chunk * kSoftmaxChunk, i1 = min(N, i0 + kSoftmaxChunk);
+    __shared__ float sm[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float m = -INFINITY;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmaxf(m, x[i]);
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) m = fmaxf(m, x[i]);
     m = warp_max(m);
-    if (lane == 0) smax[warp] = m;
+    if (lane == 0) sm[warp] = m;
     __syncthreads();
-    m = smax[0];
-    for (int w = 1; w < nw; ++w) m = fmaxf(m, smax[w]);
-    double s = 0.0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s += (double)expf(x[i] - m);
-    s = warp_sum(s);
-    if (lane == 0) ssum[warp] = s;
+    m = sm[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
     __syncthreads();
-    s = 0.0;
-    for (int w = 0; w < nw; ++w) s += ssum[w];
-    const float lse = m + (float)log(s);
+    float z = 0.f;
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) z += expf(x[i] - m);
+    z = warp_sum(z);
+    if (lane == 0) sm[warp] = z;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        z = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) z += sm[w];
+        partials[row * nchunks + chunk] = make_float2(m, z);
+    }
+}
+
+__global__ void __launch_bounds__(256) emission_softmax_write(int N, const float *__restrict__ theta,
+                                                              const float2 *__restrict__ partials,
+                                                              float *__restrict__ logE, double *__restrict__ row_sum) {
+    const int row = blockIdx.x, chunk = blockIdx.y, nchunks = gridDim.y;
+    float m = -INFINITY;
+    for (int c = 0; c < nchunks; ++c) m = fmaxf(m, partials[row * nchunks + c].x);
+    double z = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+        const float2 pz = partials[row * nchunks + c];
+        z += (double)pz.y * (double)expf(pz.x - m);
+    }
+    const float lse = m + (float)log(z);
+    const float *x = theta + (size_t)row * N;
+    float *y = logE + (size_t)row * N;
+    const int i0 = chunk * kSoftmaxChunk, i1 = min(N, i0 + kSoftmaxChunk);
     double r = 0.0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
         const float v = x[i] - lse;
         y[i] = v;
-        r += exp((double)v);
+        r += (double)expf(v);
     }
-    __syncthreads();
     r = warp_sum(r);
-    if (lane == 0) ssum[warp] = r;
+    __shared__ double sm[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sm[warp] = r;
     __syncthreads();
     if (threadIdx.x == 0) {
         r = 0.0;
-        for (int w = 0; w < nw; ++w) r += ssum[w];
-        row_lse[blockIdx.x] = log(r);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += sm[w];
+        atomicAdd(&row_sum[row], r);
     }
 }
 
 // --------------------------------------------------------------------------------------------------
-// Small forward (one CTA): the three small log_softmaxes, the mixed TPM, the log-domain hidden
-// recurrence exactly as the reference writes it (lse over the source state), G and C.
+// Small forward (one CTA): the three small log_softmaxes, the mixed TPM, the hidden-state recurrence
+// (one warp per lineage, float64 probability domain; hidden = log H afterwards), G and C.
 //   small layout: log_pi[S*L] | log_w[L] | log_A[L*S*S] | log_Amix[S*S]
 //   aux layout (floats): Hbar[S*L] | logC[S*L] | logc[S] | logq[L] | sparsity[1]
 struct SmallOffsets {
@@ -107,12 +134,13 @@ struct AuxOffsets {
     }
 };
 
-__global__ void __launch_bounds__(256) fhmm_small_forward(int S, int L, int I, int restricted, int KP,
+__global__ void __launch_bounds__(512) fhmm_small_forward(int S, int L, int I, int restricted, int KP, int P,
                                                           const float *__restrict__ theta_pi,
                                                           const float *__restrict__ theta_w,
                                                           const float *__restrict__ theta_A, float *__restrict__ small,
                                                           float *__restrict__ hidden, float *__restrict__ G,
-                                                          float *__restrict__ aux) {
+                                                          float *__restrict__ aux, double *__restrict__ Hlin,
+                                                          double *__restrict__ Apow) {
     const SmallOffsets so(S, L);
     const AuxOffsets ao(S, L);
     float *log_pi = small + so.log_pi, *log_w = small + so.log_w, *log_A = small + so.log_A,
@@ -171,69 +199,139 @@ __global__ void __launch_bounds__(256) fhmm_small_forward(int S, int L, int I, i
         aux[ao.sparsity] = -d / (float)S;
     }
 
-    // hidden recurrence. Thread (s', l) owns one entry; S*L <= blockDim.
-    const int SL = S * L;
-    const bool own = tid < SL;
-    const int sp = own ? tid / L : 0, l = own ? tid % L : 0;
-    float hsum = 0.f;
-    if (own) {
-        const float h0 = log_pi[tid];
-        s_h[tid] = h0;
-        hidden[tid] = h0;
-        hsum = expf(h0);
+    // Hidden recurrence H_t[., l] = H_{t-1}[., l] . A_l in the probability domain, float64 (the reference iterates
+    // lse_s(hidden[t-1][s,l] + log A[l,s,s']) in float32, _FHMM.py:116-124). A is constant over t, so the I-step
+    // chain is cut into blocks of P steps:
+    //   level 1  A^1 .. A^P                      (P-1 small matrix products, block-parallel)
+    //   level 2  X_b = X_{b-1} . A^P, X_0 = pi   (ceil(I/P) dependent steps, one warp per lineage)
+    //   level 3  H_{bP+j} = X_b . A^j            (all (t,s,l) in parallel)
+    // which leaves ~P + I/P dependent steps instead of I.
+    const int SL = S * L, SS = S * S;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int NB = (I + P - 1) / P;
+    double *s_pow = reinterpret_cast<double *>(sm + ((L * SS + 2 * SL + L + 1) & ~1));  // [P][L][S][S]: A^(j+1)
+    double *s_X = s_pow + (size_t)P * L * SS;                                         // [NB][S][L] (unused if P == 1)
+    double *s_part = s_X + (P > 1 ? (size_t)NB * SL : 0);                              // [blockDim]
+    for (int i = tid; i < L * SS; i += nt) {
+        const double a = exp((double)s_logA[i]);
+        s_pow[i] = a;
+        Apow[i] = a;
     }
     __syncthreads();
-    for (int t = 0; t < I; ++t) {
-        const float *cur = s_h + (t & 1) * SL;
-        float *nxt = s_h + ((t + 1) & 1) * SL;
-        // G[t][k] from the current hidden state
-        if (restricted) {
-            if (tid < S) {
-                float g = 0.f;
-                for (int ll = 0; ll < L; ++ll) g += expf(cur[tid * L + ll] + s_logw[ll]);
-                G[(size_t)t * KP + tid] = g;
-            } else if (tid < KP) {
-                G[(size_t)t * KP + tid] = 0.f;
-            }
-        } else {
-            if (own) G[(size_t)t * KP + tid] = expf(cur[tid] + s_logw[l]);
-            else if (tid < KP) G[(size_t)t * KP + tid] = 0.f;
-        }
-        if (t + 1 < I && own) {
-            // hidden[t+1][s', l] = lse_s(hidden[t][s, l] + log A[l, s, s'])   (_FHMM.py:116-124)
-            float m = -INFINITY;
-            for (int s = 0; s < S; ++s) m = fmaxf(m, cur[s * L + l] + s_logA[(l * S + s) * S + sp]);
-            float z = 0.f;
-            for (int s = 0; s < S; ++s) z += expf(cur[s * L + l] + s_logA[(l * S + s) * S + sp] - m);
-            const float h = m + logf(z);
-            nxt[tid] = h;
-            hidden[(size_t)(t + 1) * SL + tid] = h;
-            hsum += expf(h);
+    for (int j = 1; j < P; ++j) {  // A^(j+1) = A^j . A
+        const double *prev = s_pow + (size_t)(j - 1) * L * SS;
+        double *cur = s_pow + (size_t)j * L * SS;
+        for (int i = tid; i < L * SS; i += nt) {
+            const int l = i / SS, r = (i / S) % S, c = i % S;
+            double acc = 0.0;
+            for (int k = 0; k < S; ++k) acc = fma(prev[(l * S + r) * S + k], s_pow[(l * S + k) * S + c], acc);
+            cur[i] = acc;
+            Apow[(size_t)j * L * SS + i] = acc;
         }
         __syncthreads();
     }
-    // time averages: Hbar, log C = log w + log Hbar, log c_s = log sum_l C, log q_l = log sum_s C
-    float *s_logC = s_h;  // reuse
-    if (own) {
-        const float hb = hsum / (float)I;
-        aux[ao.Hbar + tid] = hb;
-        const float lc = logf(hb) + s_logw[l];
-        aux[ao.logC + tid] = lc;
-        s_logC[tid] = lc;
+    if (warp < L) {  // level 2
+        const int l = warp;
+        const double *AP = s_pow + (size_t)(P - 1) * L * SS + (size_t)l * SS;
+        double h = lane < S ? exp((double)log_pi[lane * L + l]) : 0.0;
+        for (int b = 0; b < NB; ++b) {
+            if (lane < S) (P > 1 ? s_X : Hlin)[(size_t)b * SL + lane * L + l] = h;
+            if (b + 1 == NB) break;
+            double a0 = 0.0, a1 = 0.0;
+            int k = 0;
+            for (; k + 1 < S; k += 2) {
+                const double h0 = __shfl_sync(0xffffffffu, h, k), h1 = __shfl_sync(0xffffffffu, h, k + 1);
+                if (lane < S) {
+                    a0 = fma(h0, AP[k * S + lane], a0);
+                    a1 = fma(h1, AP[(k + 1) * S + lane], a1);
+                }
+            }
+            if (k < S) {
+                const double h0 = __shfl_sync(0xffffffffu, h, k);
+                if (lane < S) a0 = fma(h0, AP[k * S + lane], a0);
+            }
+            h = a0 + a1;
+        }
     }
     __syncthreads();
-    for (int s = tid; s < S; s += nt) {
+    // level 3 + hidden = log H
+    for (int i = tid; i < I * SL; i += nt) {
+        const int t = i / SL, sp = (i / L) % S, l = i % L;
+        const int b = t / P, j = t % P;
+        double h;
+        if (P == 1) {
+            h = Hlin[i];  // level 2 already produced every step
+        } else if (j == 0) {
+            h = s_X[(size_t)b * SL + sp * L + l];
+        } else {
+            const double *Aj = s_pow + (size_t)(j - 1) * L * SS + (size_t)l * SS;
+            const double *X = s_X + (size_t)b * SL;
+            double a0 = 0.0, a1 = 0.0;
+            int k = 0;
+            for (; k + 1 < S; k += 2) {
+                a0 = fma(X[k * L + l], Aj[k * S + sp], a0);
+                a1 = fma(X[(k + 1) * L + l], Aj[(k + 1) * S + sp], a1);
+            }
+            if (k < S) a0 = fma(X[k * L + l], Aj[k * S + sp], a0);
+            h = a0 + a1;
+        }
+        if (P > 1) Hlin[i] = h;
+        hidden[i] = h > 1e-30 ? logf((float)h) : (float)log(h);
+    }
+    __syncthreads();
+    // time average Hbar[s,l] = mean_t H_t[s,l]: groups of threads sum strided slices of t, then combine
+    {
+        const int groups = nt / SL > 0 ? nt / SL : 1;
+        const int gidx = tid / SL, e = tid % SL;
+        if (gidx < groups) {
+            double acc = 0.0;
+            for (int t = gidx; t < I; t += groups) acc += Hlin[(size_t)t * SL + e];
+            s_part[gidx * SL + e] = acc;
+        }
+        __syncthreads();
+        if (tid < SL) {
+            double acc = 0.0;
+            for (int gq = 0; gq < groups; ++gq) acc += s_part[gq * SL + tid];
+            const float hb = (float)(acc / (double)I);
+            aux[ao.Hbar + tid] = hb;
+            aux[ao.logC + tid] = logf(hb) + s_logw[tid % L];
+        }
+    }
+    // the mixing matrix G[t][k] = w_l H_t[s,l] (summed over l when the emission is shared between lineages)
+    float *s_wf = s_h + SL;  // second half of the s_h scratch: w_l
+    for (int i = tid; i < L; i += nt) s_wf[i] = expf(s_logw[i]);
+    __syncthreads();
+    if (restricted) {
+        for (int i = tid; i < I * KP; i += nt) {
+            const int t = i / KP, k = i % KP;
+            float g = 0.f;
+            if (k < S)
+                for (int ll = 0; ll < L; ++ll) g += (float)Hlin[(size_t)t * SL + k * L + ll] * s_wf[ll];
+            G[i] = g;
+        }
+    } else {
+        for (int i = tid; i < I * KP; i += nt) {
+            const int t = i / KP, k = i % KP;
+            G[i] = k < SL ? (float)Hlin[(size_t)t * SL + k] * s_wf[k % L] : 0.f;
+        }
+    }
+    __syncthreads();
+    // log c_s = log sum_l C[s,l], log q_l = log sum_s C[s,l]
+    float *s_logC = s_h;
+    for (int i = tid; i < SL; i += nt) s_logC[i] = aux[ao.logC + i];
+    __syncthreads();
+    for (int s0 = tid; s0 < S; s0 += nt) {
         float m = -INFINITY;
-        for (int ll = 0; ll < L; ++ll) m = fmaxf(m, s_logC[s * L + ll]);
+        for (int ll = 0; ll < L; ++ll) m = fmaxf(m, s_logC[s0 * L + ll]);
         float z = 0.f;
-        for (int ll = 0; ll < L; ++ll) z += expf(s_logC[s * L + ll] - m);
-        aux[ao.logc + s] = m + logf(z);
+        for (int ll = 0; ll < L; ++ll) z += expf(s_logC[s0 * L + ll] - m);
+        aux[ao.logc + s0] = m + logf(z);
     }
     for (int ll = tid; ll < L; ll += nt) {
         float m = -INFINITY;
-        for (int s = 0; s < S; ++s) m = fmaxf(m, s_logC[s * L + ll]);
+        for (int s0 = 0; s0 < S; ++s0) m = fmaxf(m, s_logC[s0 * L + ll]);
         float z = 0.f;
-        for (int s = 0; s < S; ++s) z += expf(s_logC[s * L + ll] - m);
+        for (int s0 = 0; s0 < S; ++s0) z += expf(s_logC[s0 * L + ll] - m);
         aux[ao.logq + ll] = m + logf(z);
     }
 }
@@ -288,6 +386,7 @@ fhmm_data_pass(int N, int I, int K, int tchunk, const float *__restrict__ logE, 
     __syncthreads();
     double div = 0.0;
     for (int t = t0; t < t1; ++t) {
+        float div_f = 0.f;  // per-row partial in float, promoted once per t
         const float *g = sG + (t - t0) * KP;
         float part[KP];
 #pragma unroll
@@ -300,12 +399,14 @@ fhmm_data_pass(int N, int I, int K, int tchunk, const float *__restrict__ logE, 
 #pragma unroll
             for (int k = 0; k < KP; ++k) p = fmaf(g[k], Eh[j][k], p);
             p = fmaxf(p, FLT_MIN);
-            const float lp = logf(p);
-            if (pred != nullptr && ok[j]) pred[(size_t)t * N + n] = mcol[j] + lp;
+            if (pred != nullptr) {  // forward_model output: full-precision log
+                if (ok[j]) pred[(size_t)t * N + n] = mcol[j] + logf(p);
+            }
             float r = 0.f;
             if (d > 0.f) {
-                r = d / p;
-                div += (double)(d * (logf(d) - mcol[j] - lp));  // xlogy(D,D) - D*pred  (KLDivLoss, trainer.py:139)
+                // loss pass: MUFU log2 / reciprocal (abs. error of the log ~5e-7, weighted by D whose rows sum to 1)
+                r = __fdividef(d, p);
+                div_f += d * (__logf(d) - mcol[j] - __logf(p));  // xlogy(D,D) - D*pred  (KLDivLoss, trainer.py:139)
             }
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
@@ -313,6 +414,7 @@ fhmm_data_pass(int N, int I, int K, int tchunk, const float *__restrict__ logE, 
                 part[k] = fmaf(r, Eh[j][k], part[k]);
             }
         }
+        div += (double)div_f;
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
             const float s = warp_sum(part[k]);
@@ -571,7 +673,10 @@ __global__ void fhmm_emission_grad_finish(int N, int K, const float *__restrict_
 // log-likelihood (methods.py:28-40) in closed form: z[s,l,n] = I*(logE[s,e(l),n] - lse_n logE[s,e(l),:]);
 // ll = lse_n( logmeanexp_l logmeanexp_s z ). Per-node values in float64, then one CTA reduces.
 __global__ void fhmm_ll_nodes(int S, int L, int Le, int N, int I, const float *__restrict__ logE,
-                              const double *__restrict__ row_lse, double *__restrict__ v) {
+                              const double *__restrict__ row_sum, double *__restrict__ v) {
+    __shared__ double s_rl[kMaxK];  // lse_n logE[k,:] = log(row_sum[k])
+    for (int k = threadIdx.x; k < S * Le; k += blockDim.x) s_rl[k] = log(row_sum[k]);
+    __syncthreads();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     double outer_m = -INFINITY, outer[kMaxL];
@@ -579,132 +684,269 @@ __global__ void fhmm_ll_nodes(int S, int L, int Le, int N, int I, const float *_
         const int e = Le == 1 ? 0 : l;
         double m = -INFINITY;
         for (int s = 0; s < S; ++s)
-            m = fmax(m, (double)I * ((double)logE[(size_t)(s * Le + e) * N + n] - row_lse[s * Le + e]));
+            m = fmax(m, (double)I * ((double)logE[(size_t)(s * Le + e) * N + n] - s_rl[s * Le + e]));
         double z = 0.0;
         for (int s = 0; s < S; ++s)
-            z += exp((double)I * ((double)logE[(size_t)(s * Le + e) * N + n] - row_lse[s * Le + e]) - m);
+            z += exp((double)I * ((double)logE[(size_t)(s * Le + e) * N + n] - s_rl[s * Le + e]) - m);
         outer[l] = m + log(z) - log((double)S);
         outer_m = fmax(outer_m, outer[l]);
+        if (Le == 1) {  // restricted: every lineage sees the same emission row, logmeanexp over l is the identity
+            for (int l2 = 1; l2 < L; ++l2) outer[l2] = outer[0];
+            break;
+        }
     }
     double z = 0.0;
     for (int l = 0; l < L; ++l) z += exp(outer[l] - outer_m);
     v[n] = outer_m + log(z) - log((double)L);
 }
 
-__global__ void __launch_bounds__(1024) lse_double(int N, const double *__restrict__ v, double *__restrict__ out) {
-    __shared__ double sm[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    double m = -INFINITY;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmax(m, v[i]);
+// two-level float64 log-sum-exp: per-CTA (max, sum) partials, then one small CTA combines them
+__global__ void __launch_bounds__(256) lse_partials(int N, const double *__restrict__ v, double2 *__restrict__ part) {
+    __shared__ double sm[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double x = i < N ? v[i] : -INFINITY;
+    double m = x;
     for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) sm[warp] = m;
     __syncthreads();
     m = sm[0];
-    for (int w = 1; w < nw; ++w) m = fmax(m, sm[w]);
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmax(m, sm[w]);
     __syncthreads();
-    double s = 0.0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s += exp(v[i] - m);
-    s = warp_sum(s);
-    if (lane == 0) sm[warp] = s;
+    double z = (i < N && m > -INFINITY) ? exp(x - m) : 0.0;
+    z = warp_sum(z);
+    if (lane == 0) sm[warp] = z;
     __syncthreads();
     if (threadIdx.x == 0) {
-        s = 0.0;
-        for (int w = 0; w < nw; ++w) s += sm[w];
-        out[0] = m + log(s);
+        z = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) z += sm[w];
+        part[blockIdx.x] = make_double2(m, z);
+    }
+}
+
+__global__ void __launch_bounds__(256) lse_combine(int nparts, const double2 *__restrict__ part, double *__restrict__ out) {
+    __shared__ double sm[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double m = -INFINITY;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) m = fmax(m, part[i].x);
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) sm[warp] = m;
+    __syncthreads();
+    m = sm[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmax(m, sm[w]);
+    __syncthreads();
+    double z = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) z += part[i].y * exp(part[i].x - m);
+    z = warp_sum(z);
+    if (lane == 0) sm[warp] = z;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        z = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) z += sm[w];
+        out[0] = m + log(z);
     }
 }
 
 // --------------------------------------------------------------------------------------------------
-// Small backward (one CTA): dLoss/dG and dLoss/dlogC -> w, H_t; reverse recurrence -> A, pi; the sparsity term;
-// softmax Jacobians; assembles the 8 reported scalars.
+// Backward of the hidden recurrence. With c_t[s,l] = w_l gG_t[s,l] + glogC[s,l] / (I Hbar[s,l]) the adjoint is
+//     gH_t = c_t + A_l gH_{t+1}          (gH_I = 0),
+// an affine chain cut into the same blocks of P steps as the forward pass:
+//   fhmm_bwd_local (grid = blocks, one warp per lineage): R_t = c_t + A R_{t+1} inside each block, R = 0 beyond it
+//   fhmm_small_backward (one CTA):  Y_b = gH_{(b+1)P} = R_{(b+1)P} + A^P Y_{b+1}   (ceil(I/P) dependent steps)
+//                                   gH_t = R_t + A^{(b+1)P - t} Y_b                 (all (t,s,l) in parallel)
+// then dLoss/dA[l,s,s'] = sum_t H_t[s,l] gH_{t+1}[s',l] as a parallel contraction, the sparsity term, the softmax
+// Jacobians of pi, w, A and the 8 reported scalars
 //   terms: loss, divergence, log_likelihood, sparsity, orthogonality, exclusivity, regularisation, reserved
-__global__ void __launch_bounds__(1024)
-fhmm_small_backward(int S, int L, int I, int restricted, int K, const float *__restrict__ small,
-                    const float *__restrict__ hidden, const float *__restrict__ aux, const float *__restrict__ gG,
-                    const double *__restrict__ scal, float w_sparse, float w_excl, float w_orth, float w_tpm,
-                    float *__restrict__ g_pi, float *__restrict__ g_w, float *__restrict__ g_A,
-                    float *__restrict__ terms) {
+__global__ void __launch_bounds__(512)
+fhmm_bwd_local(int S, int L, int I, int P, int restricted, int K, const float *__restrict__ small,
+               const float *__restrict__ aux, const float *__restrict__ gG, const double *__restrict__ scal,
+               float *__restrict__ R) {
     const SmallOffsets so(S, L);
     const AuxOffsets ao(S, L);
     const ScalarOffsets sc(S, L, K);
-    const float *log_pi = small + so.log_pi, *log_w = small + so.log_w, *log_A = small + so.log_A,
-                *log_Amix = small + so.log_Amix;
     extern __shared__ float sm[];
-    const int SL = S * L, SSL = S * S * L;
-    float *s_A = sm;              // [L][S][S] probabilities
-    float *s_gA = s_A + SSL;      // [L][S][S]
-    float *s_gH = s_gA + SSL;     // [2][S][L]
-    float *s_H = s_gH + 2 * SL;   // [S][L]  H_{t-1}
-    float *s_w = s_H + SL;        // [L]
-    float *s_gw = s_w + L;        // [L] d/d(prob w)
-    float *s_base = s_gw + L;     // [S][L] glogC / (I * Hbar)
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < SSL; i += nt) {
-        s_A[i] = expf(log_A[i]);
-        s_gA[i] = 0.f;
+    const int SL = S * L, SP = S | 1;
+    float *s_A = sm;  // [L][S][SP]
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < L * S * S; i += nt) s_A[(i / S) * SP + i % S] = expf(small[so.log_A + i]);
+    __syncthreads();
+    if (warp >= L) return;
+    const int l = warp;
+    const bool on = lane < S;
+    const int sl = on ? lane * L + l : 0;
+    const float base = on ? (float)scal[sc.glogC + sl] / ((float)I * fmaxf(aux[ao.Hbar + sl], FLT_MIN)) : 0.f;
+    const float wl = expf(small[so.log_w + l]);
+    const float *Arow = s_A + (l * S + (on ? lane : 0)) * SP;
+    const int kidx = restricted ? (on ? lane : 0) : sl;
+    const int t_lo = blockIdx.x * P, t_hi = min(I, t_lo + P);
+    float r_next = 0.f;
+    for (int t = t_hi - 1; t >= t_lo; --t) {
+        const float c = on ? fmaf(wl, gG[(size_t)t * K + kidx], base) : 0.f;
+        float a0 = c, a1 = 0.f;
+        if (t + 1 < t_hi) {
+            int sp = 0;
+            for (; sp + 1 < S; sp += 2) {
+                const float n0 = __shfl_sync(0xffffffffu, r_next, sp), n1 = __shfl_sync(0xffffffffu, r_next, sp + 1);
+                a0 = fmaf(Arow[sp], n0, a0);
+                a1 = fmaf(Arow[sp + 1], n1, a1);
+            }
+            if (sp < S) a0 = fmaf(Arow[sp], __shfl_sync(0xffffffffu, r_next, sp), a0);
+        }
+        r_next = on ? a0 + a1 : 0.f;
+        if (on) R[(size_t)t * SL + sl] = r_next;
     }
+}
+
+__global__ void __launch_bounds__(512)
+fhmm_small_backward(int S, int L, int I, int P, int restricted, int K, const float *__restrict__ small,
+                    const double *__restrict__ Hlin, const double *__restrict__ Apow, const float *__restrict__ aux,
+                    const float *__restrict__ gG, const double *__restrict__ scal, float w_sparse, float w_excl,
+                    float w_orth, float w_tpm, float *__restrict__ gH /* in: R, out: gH */, float *__restrict__ g_pi,
+                    float *__restrict__ g_w, float *__restrict__ g_A, float *__restrict__ terms) {
+    const SmallOffsets so(S, L);
+    const AuxOffsets ao(S, L);
+    const ScalarOffsets sc(S, L, K);
+    const float *log_pi = small + so.log_pi, *log_w = small + so.log_w, *log_Amix = small + so.log_Amix;
+    extern __shared__ float sm[];
+    const int SL = S * L, SS = S * S, SP = S | 1;
+    const int NB = (I + P - 1) / P;
+    float *s_pow = sm;                          // [P][L][S][SP]: A^(j+1), rows padded
+    float *s_gA = s_pow + (size_t)P * L * S * SP;  // [L][S][S]
+    float *s_Y = s_gA + L * SS;                 // [NB][S][L]: Y_b = gH at the first step after block b (0 for the last)
+    float *s_w = s_Y + (size_t)NB * SL;         // [L]
+    float *s_gw = s_w + L;                      // [L]
+    float *s_red = s_gw + L;                    // [blockDim]
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    for (size_t i = tid; i < (size_t)P * L * SS; i += nt) s_pow[(i / S) * SP + i % S] = (float)Apow[i];
     for (int i = tid; i < L; i += nt) {
         s_w[i] = expf(log_w[i]);
         s_gw[i] = 0.f;
     }
-    for (int i = tid; i < SL; i += nt) {
-        const float hb = fmaxf(aux[ao.Hbar + i], FLT_MIN);
-        s_base[i] = (float)scal[sc.glogC + i] / ((float)I * hb);
-    }
     __syncthreads();
-    // gH_t[s,l] = w_l * gG_t[s,l] + base[s,l] + sum_s' A[l,s,s'] gH_{t+1}[s',l]
-    // gw_l += sum_s gG_t[s,l] H_t[s,l];  gA[l,s,s'] += H_{t-1}[s,l] gH_t[s',l]
-    float gw_part = 0.f;  // thread (s,l) partial of sum_t gG*H
-    for (int t = I - 1; t >= 0; --t) {
-        float *cur = s_gH + (t & 1) * SL;
-        const float *nxt = s_gH + ((t + 1) & 1) * SL;
-        if (tid < SL) {
-            const int s = tid / L, l = tid % L;
-            const float gg = gG[(size_t)t * K + (restricted ? s : tid)];
-            const float h = expf(hidden[(size_t)t * SL + tid]);
-            gw_part = fmaf(gg, h, gw_part);
-            float g = s_w[l] * gg + s_base[tid];
-            if (t + 1 < I)
-                for (int sp = 0; sp < S; ++sp) g = fmaf(s_A[(l * S + s) * S + sp], nxt[sp * L + l], g);
-            cur[tid] = g;
-            s_H[tid] = h;  // H_t, used as H_{t-1} by the gA update of step t+1 ... see below
-        }
-        __syncthreads();
-        // gA uses H_{t}[s,l] * gH_{t+1}[s',l]: at this point s_H = H_t and nxt = gH_{t+1}
-        if (t + 1 < I)
-            for (int i = tid; i < SSL; i += nt) {
-                const int l = i / (S * S), s = (i / S) % S, sp = i % S;
-                s_gA[i] = fmaf(s_H[s * L + l], nxt[sp * L + l], s_gA[i]);
+    // dependent chain over the blocks, one warp per lineage
+    if (warp < L) {
+        const int l = warp;
+        const bool on = lane < S;
+        const int sl = on ? lane * L + l : 0;
+        const float *AProw = s_pow + ((size_t)(P - 1) * L * S + (size_t)l * S + (on ? lane : 0)) * SP;
+        float y = 0.f;  // Y_{NB-1} = 0
+        for (int b = NB - 1; b >= 0; --b) {
+            if (on) s_Y[(size_t)b * SL + sl] = y;
+            if (b == 0) break;
+            // Y_{b-1} = gH_{bP} = R_{bP} + A^{P'} Y_b, P' = steps from bP to (b+1)P (= P; block b is full unless last)
+            const int span = min(I, (b + 1) * P) - b * P;  // length of block b
+            const float *Arow = (span == P) ? AProw
+                                            : s_pow + ((size_t)(span - 1) * L * S + (size_t)l * S + (on ? lane : 0)) * SP;
+            float a0 = on ? gH[(size_t)(b * P) * SL + sl] : 0.f, a1 = 0.f;
+            int sp = 0;
+            for (; sp + 1 < S; sp += 2) {
+                const float n0 = __shfl_sync(0xffffffffu, y, sp), n1 = __shfl_sync(0xffffffffu, y, sp + 1);
+                a0 = fmaf(Arow[sp], n0, a0);
+                a1 = fmaf(Arow[sp + 1], n1, a1);
             }
-        __syncthreads();
-    }
-    // reduce gw over s
-    if (tid < SL) atomicAdd(&s_gw[tid % L], gw_part);
-    __syncthreads();
-    const float *gH0 = s_gH;  // t = 0 wrote buffer 0
-    // theta_pi: softmax over s for each l
-    for (int l = tid; l < L; l += nt) {
-        float dot = 0.f;  // sum_s glogpi[s,l], glogpi = pi * gH_0
-        for (int s = 0; s < S; ++s) dot = fmaf(expf(log_pi[s * L + l]), gH0[s * L + l], dot);
-        for (int s = 0; s < S; ++s) {
-            const float p = expf(log_pi[s * L + l]);
-            g_pi[s * L + l] = p * gH0[s * L + l] - p * dot;
+            if (sp < S) a0 = fmaf(Arow[sp], __shfl_sync(0xffffffffu, y, sp), a0);
+            y = on ? a0 + a1 : 0.f;
         }
     }
+    __syncthreads();
+    // gH_t = R_t + A^{e_b - t} Y_b for every (t, s, l), e_b = end of t's block; also gw_l = sum_{t,s} gG_t[s,l] H_t[s,l].
+    // Threads are arranged as (group, element): a thread keeps one (s, l) and strides over t.
+    {
+        const int groups = nt / SL;
+        const int gidx = tid / SL, e = tid % SL, s0 = e / L, l = e % L;
+        float gw_part = 0.f;
+        if (gidx < groups) {
+            for (int t = gidx; t < I; t += groups) {
+                const int b = t / P;
+                const int pw = min(I, (b + 1) * P) - t;  // >= 1
+                const float *Arow = s_pow + ((size_t)(pw - 1) * L * S + (size_t)l * S + s0) * SP;
+                const float *Y = s_Y + (size_t)b * SL;
+                const size_t i = (size_t)t * SL + e;
+                float a0 = gH[i], a1 = 0.f;
+                int sp = 0;
+                for (; sp + 1 < S; sp += 2) {
+                    a0 = fmaf(Arow[sp], Y[sp * L + l], a0);
+                    a1 = fmaf(Arow[sp + 1], Y[(sp + 1) * L + l], a1);
+                }
+                if (sp < S) a0 = fmaf(Arow[sp], Y[sp * L + l], a0);
+                gH[i] = a0 + a1;
+                gw_part = fmaf(gG[(size_t)t * K + (restricted ? s0 : e)], (float)Hlin[i], gw_part);
+            }
+        }
+        s_red[tid] = gw_part;
+        __syncthreads();
+        if (tid < L) {
+            float acc = 0.f;
+            for (int q = 0; q < groups * SL; ++q)
+                if ((q % SL) % L == tid) acc += s_red[q];
+            s_gw[tid] = acc;
+        }
+        __syncthreads();
+    }
+    // theta_pi: glogpi = pi * gH_0, softmax over s (per lineage)
+    for (int l = tid; l < L; l += nt) {
+        float dot = 0.f;
+        for (int s0 = 0; s0 < S; ++s0) dot = fmaf(expf(log_pi[s0 * L + l]), gH[s0 * L + l], dot);
+        for (int s0 = 0; s0 < S; ++s0) {
+            const float pi = expf(log_pi[s0 * L + l]);
+            g_pi[s0 * L + l] = pi * gH[s0 * L + l] - pi * dot;
+        }
+    }
+    // gA[l,s,s'] = sum_{t=0}^{I-2} H_t[s,l] * gH_{t+1}[s',l]: chunks of t are staged in shared memory (coalesced),
+    // every output keeps its own accumulator
+    {
+        float *s_Hc = s_pow + (size_t)L * S * SP;  // powers A^2.. are no longer needed; A^1 (first L*S*SP floats) is
+        const int TC = P > 1 ? (int)min((size_t)64, ((size_t)(P - 1) * L * S * SP) / (2 * (size_t)SL)) : 0;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};  // up to 4 outputs per thread (L*S*S <= 4 * blockDim)
+        if (TC >= 2 && L * SS <= 4 * nt) {
+            float *s_Gc = s_Hc + (size_t)TC * SL;
+            for (int t0 = 0; t0 + 1 < I; t0 += TC) {
+                const int len = min(TC, I - 1 - t0);
+                for (int i = tid; i < len * SL; i += nt) {
+                    s_Hc[i] = (float)Hlin[(size_t)t0 * SL + i];
+                    s_Gc[i] = gH[(size_t)(t0 + 1) * SL + i];
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = tid + q * nt;
+                    if (i < L * SS) {
+                        const int l = i / SS, s0 = (i / S) % S, sp = i % S;
+                        float a = acc[q];
+                        for (int t = 0; t < len; ++t) a = fmaf(s_Hc[t * SL + s0 * L + l], s_Gc[t * SL + sp * L + l], a);
+                        acc[q] = a;
+                    }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (tid + q * nt < L * SS) s_gA[tid + q * nt] = acc[q];
+        } else {
+            for (int i = tid; i < L * SS; i += nt) {
+                const int l = i / SS, s0 = (i / S) % S, sp = i % S;
+                float a0 = 0.f;
+                for (int t = 0; t + 1 < I; ++t)
+                    a0 = fmaf((float)Hlin[(size_t)t * SL + s0 * L + l], gH[(size_t)(t + 1) * SL + sp * L + l], a0);
+                s_gA[i] = a0;
+            }
+        }
+    }
+    __syncthreads();
     // theta_A: glogA = A*gA + sparsity part on the diagonal; softmax over s'
     for (int r = tid; r < L * S; r += nt) {
-        const int l = r / S, s = r % S;
-        const float diag = -w_sparse / (float)S * s_w[l] * s_A[(size_t)r * S + s] / expf(log_Amix[s * S + s]);
+        const int l = r / S, s0 = r % S;
+        const float *Ar = s_pow + (size_t)r * SP;  // A^1
+        const float diag = -w_sparse / (float)S * s_w[l] * Ar[s0] / expf(log_Amix[s0 * S + s0]);
         float sum = 0.f;
+        for (int sp = 0; sp < S; ++sp) sum += Ar[sp] * s_gA[(size_t)r * S + sp] + (sp == s0 ? diag : 0.f);
         for (int sp = 0; sp < S; ++sp) {
-            float gl = s_A[(size_t)r * S + sp] * s_gA[(size_t)r * S + sp];
-            if (sp == s) gl += diag;
-            sum += gl;
-        }
-        for (int sp = 0; sp < S; ++sp) {
-            float gl = s_A[(size_t)r * S + sp] * s_gA[(size_t)r * S + sp];
-            if (sp == s) gl += diag;
-            g_A[(size_t)r * S + sp] = gl - s_A[(size_t)r * S + sp] * sum;
+            const float gl = Ar[sp] * s_gA[(size_t)r * S + sp] + (sp == s0 ? diag : 0.f);
+            g_A[(size_t)r * S + sp] = gl - Ar[sp] * sum;
         }
     }
     if (tid == 0) {
@@ -712,9 +954,9 @@ fhmm_small_backward(int S, int L, int I, int restricted, int K, const float *__r
         float glw[kMaxL], sum = 0.f;
         for (int l = 0; l < L; ++l) {
             float g = s_w[l] * s_gw[l];
-            for (int s = 0; s < S; ++s) {
-                g += (float)scal[sc.glogC + s * L + l];
-                g += -w_sparse / (float)S * s_w[l] * s_A[(l * S + s) * S + s] / expf(log_Amix[s * S + s]);
+            for (int s0 = 0; s0 < S; ++s0) {
+                g += (float)scal[sc.glogC + s0 * L + l];
+                g += -w_sparse / (float)S * s_w[l] * s_pow[(size_t)(l * S + s0) * SP + s0] / expf(log_Amix[s0 * S + s0]);
             }
             glw[l] = g;
             sum += g;
@@ -724,7 +966,7 @@ fhmm_small_backward(int S, int L, int I, int restricted, int K, const float *__r
         const float divergence = (float)scal[sc.div];
         const float sparsity = aux[ao.sparsity];
         float orth = 0.f;
-        for (int s = 0; s < S; ++s) orth += (float)scal[sc.KL + s];
+        for (int s0 = 0; s0 < S; ++s0) orth += (float)scal[sc.KL + s0];
         orth /= (float)S;
         float excl = 0.f;
         if (L > 1) {
@@ -757,20 +999,44 @@ int round_kp(int K) {
 }
 
 struct FhmmWs {
-    size_t logE, row_lse, hidden, G, small, aux, gG, split, X1, X2, Y1, TP, scal, llv, total;
-    int KP, nsplit, tchunk;
+    size_t logE, row_lse, hidden, G, small, aux, gG, split, X1, X2, Y1, TP, scal, llv, Hlin, gH, partials, llpart, Apow, total;
+    int KP, nsplit, tchunk, P;
+    size_t smem_fwd, smem_bwd, smem_local;
 };
 
 size_t up(size_t x) { return (x + 255) / 256 * 256; }
 
+// Block length of the recurrence decomposition: ~sqrt(I), bounded by the shared memory the powers A^1..A^P need
+int choose_block(int S, int L, int I, size_t *smem_fwd, size_t *smem_bwd) {
+    const size_t budget = 200 * 1024;
+    int P = 1;
+    while ((P + 1) * (P + 1) <= I) ++P;
+    for (;; --P) {
+        const size_t NB = (size_t)(I + P - 1) / P;
+        const size_t f = sizeof(float) * (size_t)((L * S * S + 2 * S * L + L + 1) & ~1) +
+                         sizeof(double) * ((size_t)P * L * S * S + (P > 1 ? NB * S * L : 0) + 512);
+        const size_t b = sizeof(float) * ((size_t)P * L * S * (S | 1) + (size_t)L * S * S + NB * S * L + 2 * L + 512);
+        if ((f <= budget && b <= budget) || P == 1) {
+            *smem_fwd = f;
+            *smem_bwd = b;
+            return P;
+        }
+    }
+}
+
 FhmmWs fhmm_layout(int S, int L, int Le, int N, int I) {
     FhmmWs w;
     const int K = S * Le;
+    w.P = choose_block(S, L, I, &w.smem_fwd, &w.smem_bwd);
+    w.smem_local = sizeof(float) * (size_t)L * S * (S | 1);
     w.KP = round_kp(K);
-    // t-splits: enough CTAs to fill the machine, G chunk <= 32 KB of shared memory
+    // t-splits: the data pass runs 128-thread CTAs at 4 per SM (J = 4 variants are register-limited), so aim at
+    // whole waves of 148 * 4 CTAs (the first capture ran 1.66 waves: 40% of the second wave idle);
+    // the G chunk of a split must fit 32 KB of shared memory
     const int J = w.KP <= 12 ? 4 : (w.KP <= 24 ? 2 : 1);
     const int tiles = (N + 128 * J - 1) / (128 * J);
-    int nsplit = (148 * 6 + tiles - 1) / tiles;
+    const int wave = 148 * 4;
+    int nsplit = tiles >= wave ? 1 : wave / tiles;
     if (nsplit < 1) nsplit = 1;
     if (nsplit > I) nsplit = I;
     int tchunk = (I + nsplit - 1) / nsplit;
@@ -799,6 +1065,11 @@ FhmmWs fhmm_layout(int S, int L, int Le, int N, int I) {
     w.TP = take(sizeof(float) * (size_t)N * L);
     w.scal = take(sizeof(double) * ScalarOffsets(S, L, K).total);
     w.llv = take(sizeof(double) * (size_t)N);
+    w.Hlin = take(sizeof(double) * (size_t)I * S * L);
+    w.gH = take(sizeof(float) * (size_t)I * S * L);
+    w.partials = take(sizeof(float2) * (size_t)K * ((N + kSoftmaxChunk - 1) / kSoftmaxChunk));
+    w.llpart = take(sizeof(double2) * (size_t)((N + 255) / 256));
+    w.Apow = take(sizeof(double) * (size_t)w.P * L * S * S);
     w.total = off;
     return w;
 }
@@ -828,7 +1099,7 @@ void dispatch_data_pass(int N, int I, int K, const FhmmWs &w, const float *logE,
 
 int32_t check_dims(int S, int L, int N, int I, int restricted) {
     CY2P_REQUIRE(S >= 1 && L >= 1 && N >= 1 && I >= 1, "S, L, N, I must be >= 1");
-    CY2P_REQUIRE(S <= kMaxS && L <= kMaxL && S * L <= 256, "supported sizes: S <= 64, L <= 16, S*L <= 256");
+    CY2P_REQUIRE(S <= kMaxS && L <= kMaxL, "supported sizes: S <= 32, L <= 16");
     CY2P_REQUIRE(S * (restricted ? 1 : L) <= kMaxK, "supported sizes: S*(restricted ? 1 : L) <= 64");
     return CY2P_OK;
 }
@@ -838,14 +1109,23 @@ int32_t run_forward(int S, int L, int Le, int N, int I, int restricted, const fl
                     const float *theta_E, const float *theta_A, const FhmmWs &w, char *ws, cudaStream_t st) {
     const int K = S * Le;
     float *logE = (float *)(ws + w.logE);
+    const int nchunks = (N + kSoftmaxChunk - 1) / kSoftmaxChunk;
+    CY2P_CUDA(cudaMemsetAsync(ws + w.row_lse, 0, sizeof(double) * K, st));
     count_launch();
-    emission_logsoftmax<<<K, 1024, 0, st>>>(N, theta_E, logE, (double *)(ws + w.row_lse));
-    const size_t smem = sizeof(float) * ((size_t)L * S * S + 2 * (size_t)S * L + L);
-    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    emission_softmax_partials<<<dim3(K, nchunks), 256, 0, st>>>(N, theta_E, (float2 *)(ws + w.partials));
     count_launch();
-    fhmm_small_forward<<<1, 256, smem, st>>>(S, L, I, restricted, w.KP, theta_pi, theta_w, theta_A,
-                                             (float *)(ws + w.small), (float *)(ws + w.hidden), (float *)(ws + w.G),
-                                             (float *)(ws + w.aux));
+    emission_softmax_write<<<dim3(K, nchunks), 256, 0, st>>>(N, theta_E, (const float2 *)(ws + w.partials), logE,
+                                                              (double *)(ws + w.row_lse));
+    if (w.smem_fwd > 220 * 1024 || w.smem_bwd > 220 * 1024) {
+        set_error("model too large for the one-CTA recurrence kernels (S=%d, L=%d, I=%d)", S, L, I);
+        return CY2P_ERR_INVALID_ARG;
+    }
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_fwd));
+    count_launch();
+    fhmm_small_forward<<<1, 512, w.smem_fwd, st>>>(S, L, I, restricted, w.KP, w.P, theta_pi, theta_w, theta_A,
+                                                   (float *)(ws + w.small), (float *)(ws + w.hidden),
+                                                   (float *)(ws + w.G), (float *)(ws + w.aux), (double *)(ws + w.Hlin),
+                                                   (double *)(ws + w.Apow));
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }
@@ -959,16 +1239,25 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
     count_launch();
     fhmm_ll_nodes<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(S, L, Le, N, I, logE, (const double *)(ws + w.row_lse),
                                                                (double *)(ws + w.llv));
+    const int nparts = (N + 255) / 256;
     count_launch();
-    lse_double<<<1, 1024, 0, st>>>(N, (const double *)(ws + w.llv), scal + sc.ll);
+    lse_partials<<<nparts, 256, 0, st>>>(N, (const double *)(ws + w.llv), (double2 *)(ws + w.llpart));
+    count_launch();
+    lse_combine<<<1, 256, 0, st>>>(nparts, (const double2 *)(ws + w.llpart), scal + sc.ll);
     // small backward
-    const size_t smem = sizeof(float) * (2 * (size_t)S * S * L + 4 * (size_t)S * L + 2 * L);
-    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int NB = (I + w.P - 1) / w.P;
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_local));
     count_launch();
-    fhmm_small_backward<<<1, 1024, smem, st>>>(S, L, I, restricted, K, (const float *)(ws + w.small),
-                                               (const float *)(ws + w.hidden), (const float *)(ws + w.aux),
-                                               (const float *)(ws + w.gG), scal, w_sparse, w_excl, w_orth, w_tpm, d_gpi,
-                                               d_gw, d_gA, d_terms);
+    fhmm_bwd_local<<<NB, L * 32, w.smem_local, st>>>(S, L, I, w.P, restricted, K, (const float *)(ws + w.small),
+                                                     (const float *)(ws + w.aux), (const float *)(ws + w.gG), scal,
+                                                     (float *)(ws + w.gH));
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bwd));
+    count_launch();
+    fhmm_small_backward<<<1, 512, w.smem_bwd, st>>>(S, L, I, w.P, restricted, K, (const float *)(ws + w.small),
+                                                    (const double *)(ws + w.Hlin), (const double *)(ws + w.Apow),
+                                                    (const float *)(ws + w.aux), (const float *)(ws + w.gG), scal,
+                                                    w_sparse, w_excl, w_orth, w_tpm, (float *)(ws + w.gH), d_gpi, d_gw,
+                                                    d_gA, d_terms);
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }

@@ -26,7 +26,7 @@ void set_error(const char *fmt, ...) {
 
 // ---------------------------------------------------------------- validation + degree statistics
 // flags[0] = first error code (0 ok), flags[1] = offending row/entry, flags[2] = max out-degree,
-// flags[3] = max in-degree, flags[4] = CDF width W, flags[5] = a row longer than W exists
+// flags[3] = max in-degree, flags[4] = CDF width W, flags[5] = some row is not strictly increasing in its column indices
 __global__ void validate_rows_kernel(int32_t n, int64_t nnz, const int32_t *__restrict__ indptr, int32_t *flags) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && (indptr[0] != 0 || (int64_t)indptr[n] != nnz)) atomicCAS(&flags[0], 0, 1);
@@ -94,6 +94,7 @@ __global__ void cdf_width_kernel(int32_t n, const int32_t *__restrict__ indptr, 
         if (strictly_increasing) {
             for (int32_t p = s; p < e; ++p) cnt += data[p] != 0.f;
         } else {  // duplicates / unsorted: O(len^2), rows are short
+            atomicExch(&flags[5], 1);
             for (int32_t p = s; p < e; ++p) {
                 bool first = true;
                 for (int32_t q = s; q < p; ++q) first &= indices[q] != indices[p];
@@ -290,6 +291,7 @@ static int32_t plan_build(int32_t n, int64_t nnz, const int32_t *indptr, const i
     plan->max_out_deg = h_flags[2];
     plan->max_in_deg = h_flags[3];
     plan->W = h_flags[4];
+    plan->canonical_rows = h_flags[5] == 0;
     free_tmp();
     *out = plan;
     return CY2P_OK;

@@ -1,88 +1,116 @@
-// K2 — Markov-chain sampling by warp-cooperative inverse-CDF search (reference simulation.py:57-87)
+// K2 — Markov-chain sampling by lane-cooperative inverse-CDF search (reference simulation.py:57-87)
 // and K2b — the per-step empirical state histogram (reference simulation.py:156-162).
 //
-// One warp walks one chain. Per step the warp reads the CDF row and the index row of the current
-// state with one coalesced load each (lane = table column), compares the step's uniform against
-// the row in float64 — numpy>=2 promotes `np.float64 <= float32[]` to float64 —
-// and the first set bit of the ballot is the reference's `np.where(...)[0][0]`. Rows wider than 32
-// are searched in 32-column chunks, stopping at the first chunk with a hit. Uniforms are fetched 32
-// steps at a time (one coalesced 256-byte read per warp) and states/probabilities are written back
-// 32 steps at a time, so the streaming traffic is coalesced although the walk itself is a chain of
-// dependent loads.
+// A group of LANES (8, 16 or 32) lanes walks one chain, so a warp carries 32/LANES chains. Per step the
+// group reads the CDF row and the index row of the current state LANES columns at a time (coalesced),
+// compares the step's uniform against the row in float64 — numpy>=2 promotes `np.float64 <= float32[]`
+// to float64 — and the first set bit of the group's ballot is the reference's
+// `np.where(...)[0][0]`; the search stops at the first chunk with a hit. Uniforms are fetched LANES steps at a
+// time and states/probabilities written LANES steps at a time, so the streaming traffic is coalesced although
+// the walk itself is a chain of dependent loads. The first ncu capture showed the 32-lane version to be
+// instruction-issue bound (82% issue slots): the narrow groups divide the per-step scalar work (shuffles,
+// ballot, address arithmetic) among 2-4 chains per warp.
+//
+// T[prev, next]: for matrices whose rows have strictly increasing columns (scipy-canonical; checked at plan
+// creation) column j of the table IS entry j of the CSR row, so the probability is data[indptr[prev] + j].
+// Otherwise (duplicate / unsorted columns) the row is scanned and duplicates are summed in storage order,
+// which is what scipy's scalar indexing returns.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cy2p {
 
+template <int LANES, bool CANONICAL>
 __global__ void __launch_bounds__(256)
 sample_chains_kernel(int64_t C, int32_t steps, int32_t W, const int32_t *__restrict__ idx,
                      const float *__restrict__ cum, const int32_t *__restrict__ indptr,
                      const int32_t *__restrict__ indices, const float *__restrict__ data,
                      const int32_t *__restrict__ init_state, const double *__restrict__ uniforms,
                      int32_t *__restrict__ states, float *__restrict__ probs, int32_t *err) {
+    constexpr int GROUPS = 32 / LANES;
     const int lane = threadIdx.x & 31;
-    const int64_t chain = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (chain >= C) return;
-    const double *u = uniforms + chain * (int64_t)steps;
-    int32_t *out_s = states + chain * ((int64_t)steps + 1);
-    float *out_p = probs + chain * (int64_t)steps;
+    const int gl = lane % LANES;             // lane within the group
+    const int gshift = (lane / LANES) * LANES;  // first lane of the group
+    const unsigned gmask = (unsigned)((LANES == 32 ? 0xffffffffull : ((1ull << LANES) - 1ull)) << gshift);
+    const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t chain = warp_global * GROUPS + lane / LANES;
+    const bool live = chain < C;
+    const int64_t ch = live ? chain : 0;
+    const double *u = uniforms + ch * (int64_t)steps;
+    int32_t *out_s = states + ch * ((int64_t)steps + 1);
+    float *out_p = probs + ch * (int64_t)steps;
 
-    int32_t state = init_state[chain];
-    if (lane == 0) out_s[0] = state;
-    bool dead = false;
+    int32_t state = init_state[ch];
+    if (live && gl == 0) out_s[0] = state;
+    bool dead = !live;
 
-    for (int32_t k0 = 0; k0 < steps; k0 += 32) {
-        const int32_t m = min(32, steps - k0);
-        const double my_u = (lane < m) ? u[k0 + lane] : 0.0;
+    for (int32_t k0 = 0; k0 < steps; k0 += LANES) {
+        const int32_t m = min(LANES, steps - k0);
+        const double my_u = (live && gl < m) ? u[k0 + gl] : 0.0;
         int32_t my_state = -1;
         float my_prob = 0.f;
-        for (int32_t s = 0; s < m && !dead; ++s) {
-            const double r = __shfl_sync(0xffffffffu, my_u, s);
+        for (int32_t s = 0; s < m; ++s) {
+            const double r = __shfl_sync(0xffffffffu, my_u, gshift + s);
             const int64_t base = (int64_t)state * W;
-            int32_t nxt = -1;
-            for (int32_t c0 = 0; c0 < W; c0 += 32) {
-                const int32_t c = c0 + lane;
-                const bool in = c < W;
+            int32_t nxt = -1, col = 0;
+            // chunked first-hit search; all groups of the warp iterate together until each has finished
+            bool searching = !dead;
+            for (int32_t c0 = 0; c0 < W; c0 += LANES) {
+                const int32_t c = c0 + gl;
+                const bool in = searching && c < W;
                 const float cv = in ? __ldg(cum + base + c) : 0.f;
                 const int32_t iv = in ? __ldg(idx + base + c) : 0;
-                const unsigned hit = __ballot_sync(0xffffffffu, in && (r <= (double)cv));
-                if (hit) {
-                    nxt = __shfl_sync(0xffffffffu, iv, __ffs(hit) - 1);
-                    break;
+                const unsigned hit = (__ballot_sync(0xffffffffu, in && (r <= (double)cv)) & gmask) >> gshift;
+                const int first = hit ? __ffs(hit) - 1 : 0;
+                const int32_t got = __shfl_sync(0xffffffffu, iv, gshift + first);
+                if (searching && hit) {
+                    nxt = got;
+                    col = c0 + first;
+                    searching = false;
                 }
+                if (!__any_sync(0xffffffffu, searching)) break;
             }
-            if (nxt < 0) {  // r above every CDF entry of the row: the reference raises IndexError here
-                if (lane == 0 && atomicCAS(&err[0], 0, 1) == 0) {
+            if (!dead && nxt < 0) {  // r above every CDF entry of the row: the reference raises IndexError here
+                if (gl == 0 && atomicCAS(&err[0], 0, 1) == 0) {
                     err[1] = (int32_t)min(chain, (int64_t)INT32_MAX);
                     err[2] = k0 + s + 1;
                     err[3] = state;
                 }
                 dead = true;
-                break;
             }
-            // T[prev, next]: sum of the stored entries of row `prev` whose column is `next`, in
-            // storage order (scipy scalar indexing sums duplicates)
-            const int32_t rb = __ldg(indptr + state), re = __ldg(indptr + state + 1);
             float pr = 0.f;
-            for (int32_t p0 = rb; p0 < re; p0 += 32) {
-                const int32_t p = p0 + lane;
-                const bool match = p < re && __ldg(indices + p) == nxt;
-                const float v = match ? __ldg(data + p) : 0.f;
-                unsigned mm = __ballot_sync(0xffffffffu, match);
-                while (mm) {  // ascending entry order
-                    const int src = __ffs(mm) - 1;
-                    pr = __fadd_rn(pr, __shfl_sync(0xffffffffu, v, src));
-                    mm &= mm - 1;
+            if (CANONICAL) {
+                if (!dead && gl == 0) pr = __ldg(data + __ldg(indptr + state) + col);
+                pr = __shfl_sync(0xffffffffu, pr, gshift);
+            } else {
+                // sum of the stored entries of row `prev` whose column is `next`, in storage order
+                // (one chain per warp on this path, so the loops below are warp-uniform)
+                static_assert(CANONICAL || LANES == 32, "the duplicate-summing path runs one chain per warp");
+                const int32_t rb = dead ? 0 : __ldg(indptr + state), re = dead ? 0 : __ldg(indptr + state + 1);
+                for (int32_t p0 = rb; p0 < re; p0 += 32) {
+                    const int32_t p = p0 + lane;
+                    const bool match = p < re && __ldg(indices + p) == nxt;
+                    const float v = match ? __ldg(data + p) : 0.f;
+                    unsigned mm = __ballot_sync(0xffffffffu, match);
+                    while (mm) {  // ascending entry order
+                        const int src = __ffs(mm) - 1;
+                        pr = __fadd_rn(pr, __shfl_sync(0xffffffffu, v, src));
+                        mm &= mm - 1;
+                    }
                 }
             }
-            state = nxt;
-            if (lane == s) {
-                my_state = nxt;
-                my_prob = pr;
+            if (!dead) {
+                state = nxt;
+                if (gl == s) {
+                    my_state = nxt;
+                    my_prob = pr;
+                }
             }
         }
-        if (lane < m) {
-            out_s[k0 + 1 + lane] = my_state;  // -1 marks steps after an overshoot
-            out_p[k0 + lane] = my_prob;
+        if (live && gl < m) {
+            out_s[k0 + 1 + gl] = my_state;  // -1 marks steps after an overshoot
+            out_p[k0 + gl] = my_prob;
         }
     }
 }
@@ -105,6 +133,19 @@ __global__ void hist_normalise_kernel(int64_t total, int64_t C, const int32_t *_
     hist[t] = (float)((double)counts[t] / (double)C);
 }
 
+template <int LANES, bool CANONICAL>
+static void launch_sampler(int64_t C, int32_t steps, int32_t W, const int32_t *idx, const float *cum,
+                           const cy2p_plan *plan, const int32_t *init_state, const double *uniforms, int32_t *states,
+                           float *probs, int32_t *err, cudaStream_t st) {
+    const int warps = 8, groups = 32 / LANES;
+    const int64_t chains_per_cta = (int64_t)warps * groups;
+    const unsigned grid = (unsigned)((C + chains_per_cta - 1) / chains_per_cta);
+    count_launch();
+    sample_chains_kernel<LANES, CANONICAL><<<grid, warps * 32, 0, st>>>(C, steps, W, idx, cum, plan->d_indptr,
+                                                                       plan->d_indices, plan->d_data, init_state,
+                                                                       uniforms, states, probs, err);
+}
+
 }  // namespace cy2p
 
 using namespace cy2p;
@@ -121,11 +162,17 @@ int32_t cy2p_sample_chains(const cy2p_plan *plan, const int32_t *d_idx, const fl
     CY2P_CUDA(cudaSetDevice(plan->device));
     CY2P_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t) * 4, st));
     if (C > 0) {
-        const int warps = 8;
-        const unsigned grid = (unsigned)((C + warps - 1) / warps);
-        count_launch(); sample_chains_kernel<<<grid, warps * 32, 0, st>>>(C, steps, W, d_idx, d_cum, plan->d_indptr, plan->d_indices,
-                                                         plan->d_data, d_init_state, d_uniforms, d_states, d_probs,
-                                                         d_err);
+        // the fast probability lookup needs table column j == CSR entry j: canonical rows no longer than W
+        const bool canonical = plan->canonical_rows && plan->max_out_deg <= W;
+        const char *ev = getenv("CY2P_SAMPLER_LANES");  // tuning knob
+        int lanes = (ev && *ev) ? atoi(ev) : (W <= 8 ? 8 : 16);
+#define CY2P_SAMPLE(L_, C_) \
+    launch_sampler<L_, C_>(C, steps, W, d_idx, d_cum, plan, d_init_state, d_uniforms, d_states, d_probs, d_err, st)
+        if (!canonical) CY2P_SAMPLE(32, false);
+        else if (lanes <= 8) CY2P_SAMPLE(8, true);
+        else if (lanes <= 16) CY2P_SAMPLE(16, true);
+        else CY2P_SAMPLE(32, true);
+#undef CY2P_SAMPLE
         CY2P_CUDA(cudaGetLastError());
     }
     int32_t h[4] = {0, 0, 0, 0};
@@ -146,8 +193,10 @@ int32_t cy2p_chain_history(const int32_t *d_states, int64_t C, int32_t ld_states
     const int64_t total = (int64_t)steps1 * n;
     CY2P_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)total, st));
     const int64_t work = C * steps1;
-    count_launch(); hist_count_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(C, ld_states, steps1, n, d_states, d_counts);
-    count_launch(); hist_normalise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, C, d_counts, d_hist);
+    count_launch();
+    hist_count_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(C, ld_states, steps1, n, d_states, d_counts);
+    count_launch();
+    hist_normalise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, C, d_counts, d_hist);
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }
