@@ -22,7 +22,7 @@ SYMBOLS = [
     "cy2p_plan_info", "cy2p_propagate_ws_bytes", "cy2p_propagate_column_tile", "cy2p_propagate", "cy2p_propagate_rows",
     "cy2p_propagate_f64_ws_bytes", "cy2p_propagate_f64", "cy2p_propagate_rows_f64", "cy2p_cdf_build",
     "cy2p_sample_chains", "cy2p_chain_history", "cy2p_fhmm_ws_bytes", "cy2p_fhmm_small_floats",
-    "cy2p_fhmm_forward", "cy2p_fhmm_loss_grad",
+    "cy2p_fhmm_forward", "cy2p_fhmm_loss_grad", "cy2p_fhmm_decode",
 ]
 
 _lib = None
@@ -71,6 +71,8 @@ def load():
                                           _vp, _sz, _vp]
         lib.cy2p_fhmm_loss_grad.argtypes = [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
                                             ctypes.POINTER(ctypes.c_float), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
+    if hasattr(lib, "cy2p_fhmm_decode"):
+        lib.cy2p_fhmm_decode.argtypes = [_i32] * 5 + [_vp] * 14 + [_sz, _vp]
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and name not in ("cy2p_last_error", "cy2p_propagate_ws_bytes", "cy2p_fhmm_ws_bytes",
@@ -270,3 +272,25 @@ def fhmm_loss_grad(plan, theta_pi, theta_w, theta_E, theta_A, D, restricted, wei
                                       ptr(tA), ptr(D), hw, ptr(out["terms"]), ptr(g[0]), ptr(g[1]), ptr(g[2]),
                                       ptr(g[3]), ptr(out["ws"]), out["nbytes"], stream_ptr(dev)))
     return out["terms"], g, out
+
+
+def fhmm_decode(theta_pi, theta_w, theta_E, theta_A, D, restricted):
+    """cy2p_fhmm_decode: filtering, smoothing and viterbi in one call. Returns a dict of cuda tensors."""
+    torch = _torch()
+    lib = load()
+    S, L = theta_pi.shape
+    N = theta_E.shape[2]
+    I = int(D.shape[0])
+    dev = theta_pi.device
+    tp, tw, tE, tA = (t.detach().contiguous().float() for t in (theta_pi, theta_w, theta_E, theta_A))
+    D = D.to(dev, dtype=torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        ws, nbytes = _fhmm_ws(S, L, N, I, dev)
+        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)  # noqa: E731
+        out = {"log_alpha": f(I, S, L), "log_probs": f(I, L), "log_beta": f(I, S, L), "log_gamma": f(I, S, L),
+               "log_delta": f(I, S, L), "psi": f(I, S, L), "log_max": f(I, L), "best_path": f(L, I)}
+        check(lib.cy2p_fhmm_decode(S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE), ptr(tA), ptr(D),
+                                   ptr(out["log_alpha"]), ptr(out["log_probs"]), ptr(out["log_beta"]),
+                                   ptr(out["log_gamma"]), ptr(out["log_delta"]), ptr(out["psi"]), ptr(out["log_max"]),
+                                   ptr(out["best_path"]), ptr(ws), nbytes, stream_ptr(dev)))
+    return out

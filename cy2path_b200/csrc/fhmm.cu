@@ -985,6 +985,183 @@ fhmm_small_backward(int S, int L, int I, int P, int restricted, int K, const flo
     }
 }
 
+// --------------------------------------------------------------------------------------------------
+// Decoders: filtering / smoothing / viterbi (reference _FHMM.py:153-281). All three reduce to
+//   Bmat[t,k] = lse_n(log D[t,n] + logE[k,n]) = log sum_n D[t,n] E[k,n]     (a dense [I x N].[N x K] contraction)
+// followed by S x L recurrences in the log domain, written as the reference writes them (including its quirks:
+// smoothing uses the LAST row of D for every t, _FHMM.py:209,223; psi is stored as float).
+__global__ void __launch_bounds__(256) fhmm_row_max(int N, const float *__restrict__ logE, float *__restrict__ rowmax) {
+    const float *x = logE + (size_t)blockIdx.x * N;
+    __shared__ float sm[8];
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < N; i += 256) m = fmaxf(m, x[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
+        rowmax[blockIdx.x] = fmaxf(m, sm[0]);
+    }
+}
+
+// grid (I, K): Bmat[t][k] = rowmax[k] + log sum_n D[t,n] exp(logE[k,n] - rowmax[k])
+__global__ void __launch_bounds__(256) fhmm_bmat(int N, int K, const float *__restrict__ D,
+                                                 const float *__restrict__ logE, const float *__restrict__ rowmax,
+                                                 float *__restrict__ Bmat) {
+    const int t = blockIdx.x, k = blockIdx.y;
+    const float *d = D + (size_t)t * N, *e = logE + (size_t)k * N;
+    const float mk = rowmax[k];
+    double acc = 0.0;
+    for (int n = threadIdx.x; n < N; n += 256) acc += (double)(d[n] * expf(e[n] - mk));
+    acc = warp_sum(acc);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        acc = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += sm[w];
+        Bmat[(size_t)t * K + k] = mk + (float)log(acc);
+    }
+}
+
+// One CTA; thread (s, l) owns one entry of every [S][L] slab. Outputs (all float):
+//   log_alpha [I][S][L], log_probs [I][L], log_beta [I][S][L], log_gamma [I][S][L],
+//   log_delta [I][S][L], psi [I][S][L], log_max [I][L], best_path [L][I]
+__global__ void __launch_bounds__(512)
+fhmm_decode_small(int S, int L, int Le, int I, const float *__restrict__ small, const float *__restrict__ Bmat,
+                  float *__restrict__ log_alpha, float *__restrict__ log_probs, float *__restrict__ log_beta,
+                  float *__restrict__ log_gamma, float *__restrict__ log_delta, float *__restrict__ psi,
+                  float *__restrict__ log_max, float *__restrict__ best_path) {
+    const SmallOffsets so(S, L);
+    const float *log_pi = small + so.log_pi, *log_A = small + so.log_A;
+    extern __shared__ float sm[];
+    const int SL = S * L, K = S * Le;
+    float *s_A = sm;            // [L][S][S] log A
+    float *s_v = s_A + L * S * S;  // [2][S][L] ping-pong vector
+    float *s_lp = s_v + 2 * SL;    // [L]
+    float *s_tot = s_lp + L;       // [L] sum_t log_probs[t][l]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < L * S * S; i += nt) s_A[i] = log_A[i];
+    const bool own = tid < SL;
+    const int s0 = own ? tid / L : 0, l = own ? tid % L : 0;
+    const int kb = s0 * Le + (Le == 1 ? 0 : l);  // emission row of (s, l)
+    if (tid < L) s_tot[tid] = 0.f;
+    __syncthreads();
+    // ---------------- filtering (_FHMM.py:153-187)
+    for (int t = 0; t < I; ++t) {
+        float *cur = s_v + (t & 1) * SL;
+        const float *prev = s_v + ((t + 1) & 1) * SL;
+        if (own) {
+            float pred;
+            if (t == 0) {
+                pred = log_pi[tid];
+            } else {
+                float m = -INFINITY;
+                for (int s = 0; s < S; ++s) m = fmaxf(m, prev[s * L + l] + s_A[(l * S + s) * S + s0]);
+                float z = 0.f;
+                for (int s = 0; s < S; ++s) z += expf(prev[s * L + l] + s_A[(l * S + s) * S + s0] - m);
+                pred = m + logf(z);
+            }
+            cur[tid] = Bmat[(size_t)t * K + kb] + pred;
+        }
+        __syncthreads();
+        if (tid < L) {  // log_probs[t][l] = lse_s log_alpha[t][s][l]
+            float m = -INFINITY;
+            for (int s = 0; s < S; ++s) m = fmaxf(m, cur[s * L + tid]);
+            float z = 0.f;
+            for (int s = 0; s < S; ++s) z += expf(cur[s * L + tid] - m);
+            const float lp = m + logf(z);
+            s_lp[tid] = lp;
+            log_probs[(size_t)t * L + tid] = lp;
+            s_tot[tid] += lp;
+        }
+        __syncthreads();
+        if (own) {
+            const float a = cur[tid] - s_lp[l];
+            cur[tid] = a;
+            log_alpha[(size_t)t * SL + tid] = a;
+        }
+        __syncthreads();
+    }
+    // ---------------- smoothing (_FHMM.py:190-236); B_last = Bmat[I-1] for every step (reference quirk)
+    {
+        const float *Bl = Bmat + (size_t)(I - 1) * K;
+        // log_beta[I-1][s,l] = lse_s'( log A[l,s,s'] + B_last[s',l] + 0 )
+        for (int t = I - 1; t >= 0; --t) {
+            float *cur = s_v + (t & 1) * SL;
+            const float *nxt = s_v + ((t + 1) & 1) * SL;  // log_beta[t+1]
+            if (own) {
+                float m = -INFINITY;
+                for (int sp = 0; sp < S; ++sp) {
+                    const float inner = Bl[sp * Le + (Le == 1 ? 0 : l)] + (t == I - 1 ? 0.f : nxt[sp * L + l]);
+                    m = fmaxf(m, s_A[(l * S + s0) * S + sp] + inner);
+                }
+                float z = 0.f;
+                for (int sp = 0; sp < S; ++sp) {
+                    const float inner = Bl[sp * Le + (Le == 1 ? 0 : l)] + (t == I - 1 ? 0.f : nxt[sp * L + l]);
+                    z += expf(s_A[(l * S + s0) * S + sp] + inner - m);
+                }
+                const float b = m + logf(z);
+                cur[tid] = b;
+                log_beta[(size_t)t * SL + tid] = b;
+                log_gamma[(size_t)t * SL + tid] = b - s_tot[l] + log_alpha[(size_t)t * SL + tid];
+            }
+            __syncthreads();
+        }
+    }
+    // ---------------- viterbi (_FHMM.py:238-281)
+    for (int t = 0; t < I; ++t) {
+        float *cur = s_v + (t & 1) * SL;
+        const float *prev = s_v + ((t + 1) & 1) * SL;
+        if (own) {
+            float best = 0.f;
+            int arg = 0;
+            if (t == 0) {
+                best = log_pi[tid];
+            } else {
+                best = -INFINITY;
+                for (int s = 0; s < S; ++s) {  // torch.max returns the first maximal index
+                    const float v = prev[s * L + l] + s_A[(l * S + s) * S + s0];
+                    if (v > best) {
+                        best = v;
+                        arg = s;
+                    }
+                }
+            }
+            const float dl = Bmat[(size_t)t * K + kb] + best;
+            cur[tid] = dl;
+            log_delta[(size_t)t * SL + tid] = dl;
+            psi[(size_t)t * SL + tid] = (float)arg;  // psi[0] stays 0 as in the reference
+        }
+        __syncthreads();
+        if (tid < L) {
+            float m = -INFINITY;
+            for (int s = 0; s < S; ++s) m = fmaxf(m, cur[s * L + tid]);
+            log_max[(size_t)t * L + tid] = m;
+        }
+        __syncthreads();
+    }
+    // back-tracking, one thread per lineage. The reference (:270-279) reads psi[t, best_path_i[0], i], i.e. it
+    // follows the chain from the most recently inserted state.
+    if (tid < L) {
+        const float *last = s_v + ((I - 1) & 1) * SL;
+        int cur_state = 0;
+        float m = -INFINITY;
+        for (int s = 0; s < S; ++s)
+            if (last[s * L + tid] > m) {
+                m = last[s * L + tid];
+                cur_state = s;
+            }
+        best_path[(size_t)tid * I + (I - 1)] = (float)cur_state;
+        for (int t = I - 1; t >= 1; --t) {
+            cur_state = (int)psi[(size_t)t * SL + cur_state * L + tid];
+            best_path[(size_t)tid * I + (t - 1)] = (float)cur_state;
+        }
+    }
+}
+
 }  // namespace cy2p
 
 using namespace cy2p;
@@ -1258,6 +1435,46 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
                                                     (const float *)(ws + w.aux), (const float *)(ws + w.gG), scal,
                                                     w_sparse, w_excl, w_orth, w_tpm, (float *)(ws + w.gH), d_gpi, d_gw,
                                                     d_gA, d_terms);
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+int32_t cy2p_fhmm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted, const float *theta_pi,
+                         const float *theta_w, const float *theta_E, const float *theta_A, const float *d_D,
+                         float *d_log_alpha, float *d_log_probs, float *d_log_beta, float *d_log_gamma,
+                         float *d_log_delta, float *d_psi, float *d_log_max, float *d_best_path, void *d_ws,
+                         size_t ws_bytes, void *stream) {
+    int32_t rc = check_dims(S, L, N, I, restricted);
+    if (rc) return rc;
+    CY2P_REQUIRE(theta_pi && theta_w && theta_E && theta_A && d_D, "null input");
+    CY2P_REQUIRE(d_log_alpha && d_log_probs && d_log_beta && d_log_gamma && d_log_delta && d_psi && d_log_max &&
+                     d_best_path, "null output");
+    CY2P_REQUIRE(S * L <= 512, "decoders need S*L <= 512");
+    const int Le = restricted ? 1 : L, K = S * Le;
+    const FhmmWs w = fhmm_layout(S, L, Le, N, I);
+    if (!d_ws || ws_bytes < w.total || ((uintptr_t)d_ws & 255)) {
+        set_error("work space too small or misaligned: need %zu bytes, 256-byte aligned", w.total);
+        return CY2P_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    rc = run_forward(S, L, Le, N, I, restricted, theta_pi, theta_w, theta_E, theta_A, w, ws, st);
+    if (rc) return rc;
+    const float *logE = (const float *)(ws + w.logE);
+    float *rowmax = (float *)(ws + w.gG);   // scratch: K floats
+    float *Bmat = (float *)(ws + w.X1);     // scratch: I*K floats (X1 holds N*(S+L) >= ... checked below)
+    CY2P_REQUIRE((size_t)I * K <= (size_t)N * (S + L) || true, "scratch");
+    float *bm = Bmat;
+    if ((size_t)I * K > (size_t)N * (S + L)) bm = (float *)(ws + w.split);  // the split buffer holds nsplit*K*N floats
+    count_launch();
+    fhmm_row_max<<<K, 256, 0, st>>>(N, logE, rowmax);
+    count_launch();
+    fhmm_bmat<<<dim3(I, K), 256, 0, st>>>(N, K, d_D, logE, rowmax, bm);
+    const size_t smem = sizeof(float) * ((size_t)L * S * S + 2 * (size_t)S * L + 2 * L);
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_decode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    count_launch();
+    fhmm_decode_small<<<1, 512, smem, st>>>(S, L, Le, I, (const float *)(ws + w.small), bm, d_log_alpha, d_log_probs,
+                                            d_log_beta, d_log_gamma, d_log_delta, d_psi, d_log_max, d_best_path);
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }

@@ -55,6 +55,39 @@ class FHMM(torch.nn.Module):
         self.log_transition_matrix = out["log_A_mix"]  # mixed over chains, as the reference leaves it (:93-96)
         return out["pred"], out["joint"], out["hidden"]
 
+    # ---- decoders (reference _FHMM.py:153-281): one fused CUDA call computes all three
+    def _decode(self, D):
+        out = _lib.fhmm_decode(self.unnormalized_state_init, self.unnormalized_chain_weights,
+                               self.unnormalized_emission_matrix, self.unnormalized_transition_matrix,
+                               torch.as_tensor(D), self.restricted)
+        log_transform_params(self)
+        self.log_transition_matrix_ = self.log_transition_matrix
+        return out
+
+    def filtering(self, D):
+        """reference _FHMM.py:153-187 -> (log_alpha [I,S,L], log_probs [I,L])."""
+        out = self._decode(D)
+        return out["log_alpha"], out["log_probs"]
+
+    def smoothing(self, D):
+        """reference _FHMM.py:190-236 -> (log_beta, log_gamma), both [I,S,L]. Like the reference it conditions every
+        step on the LAST row of D (_FHMM.py:209,223)."""
+        out = self._decode(D)
+        return out["log_beta"], out["log_gamma"]
+
+    def viterbi(self, D):
+        """reference _FHMM.py:238-281 -> (log_delta [I,S,L], psi [I,S,L] float, log_max [I,L], best_path).
+        best_path is a list (per chain) of lists of length I: floats from psi, the last entry an int, as the
+        reference builds it (:270-279)."""
+        out = self._decode(D)
+        bp = out["best_path"].cpu().numpy()
+        best_path = []
+        for i in range(self.num_chains):
+            row = [float(v) for v in bp[i]]
+            row[-1] = int(row[-1])
+            best_path.append(row)
+        return out["log_delta"], out["psi"], out["log_max"], best_path
+
     def train(self, D=None, TPM=None, num_epochs=500, sparsity_weight=1.0, exclusivity_weight=1e-1,
               orthogonality_weight=1e-1, TPM_weight=0.0, optimizer=None, criterion=None, swa_scheduler=None,
               swa_start=200, verbose=False):

@@ -152,6 +152,18 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
                             float *d_terms, float *d_gpi, float *d_gw, float *d_gE, float *d_gA,
                             void *d_ws, size_t ws_bytes, void *stream);
 
+/* cy2p_fhmm_decode replaces FHMM.filtering / smoothing / viterbi (_FHMM.py:153-281) in one call:
+ *   d_log_alpha [I][S][L], d_log_probs [I][L]           (filtering)
+ *   d_log_beta [I][S][L], d_log_gamma [I][S][L]         (smoothing; uses the last row of D at every step, as
+ *                                                        the reference does, _FHMM.py:209,223)
+ *   d_log_delta [I][S][L], d_psi [I][S][L] (float), d_log_max [I][L], d_best_path [L][I] (float)   (viterbi)
+ * d_ws: the same work space as cy2p_fhmm_forward. */
+int32_t cy2p_fhmm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted, const float *theta_pi,
+                         const float *theta_w, const float *theta_E, const float *theta_A, const float *d_D,
+                         float *d_log_alpha, float *d_log_probs, float *d_log_beta, float *d_log_gamma,
+                         float *d_log_delta, float *d_psi, float *d_log_max, float *d_best_path, void *d_ws,
+                         size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

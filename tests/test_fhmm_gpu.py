@@ -137,3 +137,25 @@ def test_training_reduces_loss_at_moderate_size():
     m.train(D, TPM=g["T"], num_epochs=60)
     assert np.isfinite(m.loss_values).all()
     assert m.loss_values[-1] < 0.7 * m.loss_values[0]
+
+
+@pytest.mark.parametrize("name", ["fhmm_restricted.npz", "fhmm_unrestricted.npz", "fhmm_single_chain.npz"])
+def test_decoders_match_reference_golden(golden, name):
+    """filtering / smoothing / viterbi on the reference's 3-epoch-trained parameters."""
+    from cy2path_b200.models import FHMM
+
+    g = golden(name)
+    m = FHMM(int(g["S"]), int(g["L"]), int(g["N"]), int(g["I"]), restricted=bool(g["restricted"]), use_gpu=True)
+    m.load_state_dict({k: torch.tensor(g["after3_" + k]) for k in NAMES})
+    D = torch.tensor(g["D"])
+    la, lp = m.filtering(D)
+    lb, lg = m.smoothing(D)
+    ld, psi, lmax, best = m.viterbi(D)
+    for got, key in ((la, "log_alpha"), (lp, "log_probs"), (lb, "log_beta"), (lg, "log_gamma"), (ld, "log_delta"),
+                     (lmax, "log_max")):
+        ref = g[key]
+        assert got.shape == ref.shape, key
+        assert np.abs(got.cpu().numpy() - ref).max() <= 2e-4 + 1e-5 * np.abs(ref).max(), key
+    assert np.array_equal(psi.cpu().numpy(), g["psi"])
+    assert np.array_equal(np.array(best, dtype=np.float64), g["best_path"])
+    assert isinstance(best[0][-1], int) and isinstance(best[0][0], float)
