@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "../../include/cy2path_b200.h"
 
 namespace cy2p {
@@ -50,6 +52,8 @@ struct cy2p_plan {
     int32_t device = 0;
     int32_t num_sms = 0;
     int32_t max_in_deg = 0, max_out_deg = 0, W = 0;
+    std::vector<int32_t> h_t_indptr;  // host copy of d_t_indptr (filled on demand for small graphs)
+    int32_t cluster_ctas = 0;     // cluster size of the single-start kernel: 0 = not probed yet, -1 = unavailable
     bool canonical_rows = false;  // every row of T has strictly increasing column indices (no duplicates)
     size_t bytes_owned = 0;
     size_t l2_bytes = 0;

@@ -19,6 +19,8 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -234,6 +236,163 @@ spmv_b1_persistent(int32_t n, const int32_t *__restrict__ t_indptr, const Pair *
     }
 }
 
+// B == 1 for small graphs (the reference's typical 3-10k cell data sets): ONE thread-block cluster runs every
+// iteration; the per-update barrier is the hardware cluster barrier (~0.2 us) instead of a grid-wide one (~5 us), each
+// CTA keeps the (src,val) pairs of its destination rows in shared memory, a warp gathers four rows at a time so the
+// four L2 loads overlap, and the iterate stays in L2 (loads bypass L1, which is not coherent across SMs).
+//   eps_part: [iters][nctas * 32 warps][2] doubles written with plain stores (no atomics), or null
+template <typename T>
+__global__ void __launch_bounds__(1024)
+spmv_b1_cluster(int32_t n, const int32_t *__restrict__ t_indptr, const Pair *__restrict__ pairs, const T *x0, T *hist,
+                T *bufA, T *bufB, T *last, int32_t iters, const double *__restrict__ stationary, double *eps_part,
+                int32_t pairs_in_smem) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), nctas = (int)cluster.num_blocks();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int m = (n + nctas - 1) / nctas;
+    const int r0 = min(n, rank * m), r1 = min(n, r0 + m);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t *s_ip = reinterpret_cast<int32_t *>(smem_raw);                        // [m + 1] row pointers of my slice
+    Pair *s_pairs = reinterpret_cast<Pair *>(smem_raw + (((size_t)m + 2) / 2) * 8);  // 8-byte aligned
+    const int32_t p_base = t_indptr[r0];
+    for (int32_t i = threadIdx.x; i <= r1 - r0; i += blockDim.x) s_ip[i] = t_indptr[r0 + i];
+    if (pairs_in_smem) {
+        const int32_t cnt = t_indptr[r1] - p_base;
+        for (int32_t i = threadIdx.x; i < cnt; i += blockDim.x) s_pairs[i] = pairs[p_base + i];
+    }
+    __syncthreads();
+    const Pair *pp = pairs_in_smem ? s_pairs - p_base : pairs;  // indexable by the global entry position
+    // 8 lanes per destination row (kNN rows hold ~30 entries: 4 per lane), 4 rows per warp pass, 3 shuffle steps
+    constexpr int G = 8, RPW = 32 / G;
+    const int gl = lane % G, grp = lane / G;
+    for (int32_t it = 0; it < iters; ++it) {
+        const T *src;
+        T *dst;
+        if (hist) {
+            src = hist + (int64_t)it * n;
+            dst = (it + 1 < iters) ? hist + (int64_t)(it + 1) * n : last;
+        } else {
+            src = it == 0 ? x0 : ((it & 1) ? bufA : bufB);
+            dst = (it + 1 == iters) ? last : ((it & 1) ? bufB : bufA);
+        }
+        double uv = 0.0, uu = 0.0;
+        for (int32_t rb = r0 + warp * RPW; rb < r1; rb += nw * RPW) {
+            const int32_t r = rb + grp;
+            const bool ok = r < r1;
+            const int32_t beg = ok ? s_ip[r - r0] : 0, end = ok ? s_ip[r - r0 + 1] : 0;
+            T acc = (T)0;
+            for (int32_t p0 = beg + gl; p0 < end; p0 += 4 * G) {  // four gathers in flight per lane
+                Pair e[4];
+                T xv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int32_t p = p0 + k * G;
+                    e[k] = p < end ? pp[p] : Pair{0, 0.f};
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xv[k] = (p0 + k * G < end) ? __ldcg(src + e[k].src) : (T)0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc = fma((T)e[k].val, xv[k], acc);
+            }
+#pragma unroll
+            for (int o = G / 2; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (ok && gl == 0) {
+                dst[r] = acc;
+                if (eps_part) {
+                    const double yd = (double)acc;
+                    uv = fma(yd, stationary[r], uv);
+                    uu = fma(yd, yd, uu);
+                }
+            }
+        }
+        if (eps_part) {  // per-warp partial sums, plain stores; eps_finalize_tile adds the nctas * nw partials
+#pragma unroll
+            for (int o = 16; o >= G; o >>= 1) {
+                uv += __shfl_xor_sync(0xffffffffu, uv, o);
+                uu += __shfl_xor_sync(0xffffffffu, uu, o);
+            }
+            if (lane == 0) {
+                double *dstp = eps_part + ((int64_t)it * nctas * nw + (int64_t)rank * nw + warp) * 2;
+                dstp[0] = uv;
+                dstp[1] = uu;
+            }
+        }
+        cluster.sync();  // release/acquire at cluster scope: the new iterate is visible to every CTA of the cluster
+    }
+}
+
+// Same cluster, but the iterate itself lives in (distributed) shared memory: every CTA keeps a full double-buffered
+// copy of x, reads its gathers from its own copy (LDS instead of an L2 round trip) and pushes each new value into
+// all CTAs' copies with st.shared::cluster. The per-update barrier then only has to order shared-memory traffic: the
+// global-memory release/acquire of the variant above costs ~5 us per update on B200, this one ~1 us. The history
+// row (global) is written with plain stores; nobody reads it inside the kernel.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+spmv_b1_cluster_dsmem(int32_t n, const int32_t *__restrict__ t_indptr, const Pair *__restrict__ pairs, const T *x0,
+                      T *hist, T *last, int32_t iters, const double *__restrict__ stationary, double *eps_part) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), nctas = (int)cluster.num_blocks();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int m = (n + nctas - 1) / nctas;
+    const int r0 = min(n, rank * m), r1 = min(n, r0 + m);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s_x = reinterpret_cast<T *>(smem_raw);                                 // [2][n]
+    int32_t *s_ip = reinterpret_cast<int32_t *>(s_x + 2 * (size_t)n);         // [m + 1]
+    Pair *s_pairs = reinterpret_cast<Pair *>(reinterpret_cast<unsigned char *>(s_ip) + (((size_t)m + 2) / 2) * 8);
+    const int32_t p_base = t_indptr[r0];
+    for (int32_t i = threadIdx.x; i <= r1 - r0; i += blockDim.x) s_ip[i] = t_indptr[r0 + i];
+    const int32_t cnt = t_indptr[r1] - p_base;
+    for (int32_t i = threadIdx.x; i < cnt; i += blockDim.x) s_pairs[i] = pairs[p_base + i];
+    for (int32_t i = threadIdx.x; i < n; i += blockDim.x) s_x[i] = x0[i];
+    cluster.sync();  // every CTA's shared memory is initialised before anyone stores into it remotely
+    const Pair *pp = s_pairs - p_base;
+    constexpr int G = 8, RPW = 32 / G;
+    const int gl = lane % G, grp = lane / G;
+    for (int32_t it = 0; it < iters; ++it) {
+        const T *cur = s_x + (size_t)(it & 1) * n;
+        T *nxt_local = s_x + (size_t)((it + 1) & 1) * n;
+        T *gdst = hist ? ((it + 1 < iters) ? hist + (int64_t)(it + 1) * n : last) : (it + 1 == iters ? last : nullptr);
+        double uv = 0.0, uu = 0.0;
+        for (int32_t rb = r0 + warp * RPW; rb < r1; rb += nw * RPW) {
+            const int32_t r = rb + grp;
+            const bool ok = r < r1;
+            const int32_t beg = ok ? s_ip[r - r0] : 0, end = ok ? s_ip[r - r0 + 1] : 0;
+            T acc = (T)0;
+            for (int32_t p = beg + gl; p < end; p += G) {
+                const Pair e = pp[p];
+                acc = fma((T)e.val, cur[e.src], acc);
+            }
+#pragma unroll
+            for (int o = G / 2; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (ok) {
+                // every lane of the group holds the row sum: lane gl pushes it to CTAs gl, gl + G, ...
+                for (int dstc = gl; dstc < nctas; dstc += G) cluster.map_shared_rank(nxt_local, dstc)[r] = acc;
+                if (gl == 0) {
+                    if (gdst) gdst[r] = acc;
+                    if (eps_part) {
+                        const double yd = (double)acc;
+                        uv = fma(yd, stationary[r], uv);
+                        uu = fma(yd, yd, uu);
+                    }
+                }
+            }
+        }
+        if (eps_part) {
+#pragma unroll
+            for (int o = 16; o >= G; o >>= 1) {
+                uv += __shfl_xor_sync(0xffffffffu, uv, o);
+                uu += __shfl_xor_sync(0xffffffffu, uu, o);
+            }
+            if (lane == 0) {
+                double *dstp = eps_part + ((int64_t)it * nctas * nw + (int64_t)rank * nw + warp) * 2;
+                dstp[0] = uv;
+                dstp[1] = uu;
+            }
+        }
+        cluster.sync();
+    }
+}
+
 __global__ void sumsq_kernel(int32_t n, const double *__restrict__ v, double *out) {
     double s = 0.0;
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s = fma(v[i], v[i], s);
@@ -291,7 +450,7 @@ static WsLayout ws_layout(const cy2p_plan *plan, int32_t B, int32_t iters, size_
     w.tile = choose_tile(plan, B, elem);
     size_t off = 0;
     w.eps_acc = off;
-    off = align_up(off + sizeof(double) * 2 * (size_t)iters * (size_t)w.tile * kEpsCopies, 256);
+    off = align_up(off + sizeof(double) * 2 * (size_t)iters * ((size_t)w.tile * kEpsCopies > 512 ? (size_t)w.tile * kEpsCopies : 512), 256);
     w.vv = off;
     off = align_up(off + sizeof(double), 256);
     w.bufA = off;
@@ -366,8 +525,126 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
     if (d_history)  // row 0 of the history is the start distribution (sampling.py:39)
         CY2P_CUDA(cudaMemcpyAsync(d_history, d_X0, sizeof(T) * (size_t)n * B, cudaMemcpyDeviceToDevice, st));
 
-    // ---- B == 1: one cooperative launch for all iterations --------------------------------------
+    // ---- B == 1: all iterations in one launch --------------------------------------------------
     if (B == 1 && (!d_history || history_stride == 1)) {
+        T *last = d_Xfinal ? d_Xfinal : bufB;
+        int32_t n_ = n, iters_ = iters;
+        const int32_t *tp = plan->d_t_indptr;
+        const Pair *pp = plan->d_t_pairs;
+        // (a) small graphs: one thread-block cluster (hardware barrier per update)
+        static const int cluster_max_nnz = env_int("CY2P_CLUSTER_MAX_NNZ", 600000);
+        if (plan->nnz <= cluster_max_nnz && plan->cluster_ctas >= 0) {
+            if (plan->cluster_ctas == 0) {  // probe once per plan: largest cluster (16, then 8) that can be resident
+                plan->cluster_ctas = -1;
+                for (int c : {16, 8}) {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(c);
+                    cfg.blockDim = dim3(1024);
+                    cfg.dynamicSmemBytes = 0;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = c;
+                    at[0].val.clusterDim.y = 1;
+                    at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = 1;
+                    if (c > 8 &&
+                        cudaFuncSetAttribute(spmv_b1_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+                            cudaSuccess) {
+                        cudaGetLastError();
+                        continue;
+                    }
+                    int nclusters = 0;
+                    if (cudaOccupancyMaxActiveClusters(&nclusters, spmv_b1_cluster<T>, &cfg) == cudaSuccess &&
+                        nclusters >= 1) {
+                        plan->cluster_ctas = c;
+                        break;
+                    }
+                    cudaGetLastError();
+                }
+            }
+            const int c = plan->cluster_ctas;
+            if (c > 0) {
+                // shared memory: the row pointers of a slice + the (src,val) pairs of the fattest slice
+                const int m = (n + c - 1) / c;
+                if (plan->h_t_indptr.empty()) {
+                    plan->h_t_indptr.resize((size_t)n + 1);
+                    CY2P_CUDA(cudaMemcpyAsync(plan->h_t_indptr.data(), plan->d_t_indptr, sizeof(int32_t) * ((size_t)n + 1),
+                                              cudaMemcpyDeviceToHost, st));
+                    CY2P_CUDA(cudaStreamSynchronize(st));
+                }
+                size_t worst = 0;
+                for (int r = 0; r < c; ++r) {
+                    const int a = std::min(n, r * m), b = std::min(n, a + m);
+                    worst = std::max(worst, (size_t)(plan->h_t_indptr[b] - plan->h_t_indptr[a]));
+                }
+                const size_t ip_bytes = (((size_t)m + 2) / 2) * 8;
+                size_t smem = ip_bytes + worst * sizeof(Pair);
+                int32_t in_smem = smem <= 200 * 1024 ? 1 : 0;
+                if (!in_smem) smem = ip_bytes;
+                // (a1) iterate in distributed shared memory when two copies of x also fit
+                const size_t smem_ds = 2 * (size_t)n * sizeof(T) + ip_bytes + worst * sizeof(Pair);
+                static const int use_dsmem = env_int("CY2P_B1_DSMEM", 1);
+                if (use_dsmem && smem_ds <= 200 * 1024 && (d_history || d_Xfinal)) {
+                    if (c > 8)
+                        CY2P_CUDA(cudaFuncSetAttribute(spmv_b1_cluster_dsmem<T>,
+                                                       cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                    CY2P_CUDA(cudaFuncSetAttribute(spmv_b1_cluster_dsmem<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)smem_ds));
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(c);
+                    cfg.blockDim = dim3(1024);
+                    cfg.dynamicSmemBytes = smem_ds;
+                    cfg.stream = st;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = c;
+                    at[0].val.clusterDim.y = 1;
+                    at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = 1;
+                    double *part = d_eps ? eps_acc : nullptr;
+                    count_launch();
+                    cudaError_t le = cudaLaunchKernelEx(&cfg, spmv_b1_cluster_dsmem<T>, n_, tp, pp, d_X0, d_history, last,
+                                                        iters_, d_stationary, part);
+                    if (le == cudaSuccess) {
+                        if (d_eps) {
+                            count_launch();
+                            eps_finalize_tile<<<(iters + 255) / 256, 256, 0, st>>>(iters, c * 32, 1, 0, 1, eps_acc, vv, d_eps);
+                        }
+                        CY2P_CUDA(cudaGetLastError());
+                        return CY2P_OK;
+                    }
+                    cudaGetLastError();  // not launchable with this much shared memory per cluster: fall through
+                }
+                if (c > 8)
+                    CY2P_CUDA(cudaFuncSetAttribute(spmv_b1_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                CY2P_CUDA(cudaFuncSetAttribute(spmv_b1_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(c);
+                cfg.blockDim = dim3(1024);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = c;
+                at[0].val.clusterDim.y = 1;
+                at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                double *part = d_eps ? eps_acc : nullptr;  // [iters][c * 32][2], written with plain stores
+                count_launch();
+                CY2P_CUDA(cudaLaunchKernelEx(&cfg, spmv_b1_cluster<T>, n_, tp, pp, d_X0, d_history, bufA, bufB, last, iters_,
+                                             d_stationary, part, in_smem));
+                if (d_eps) {
+                    count_launch();
+                    eps_finalize_tile<<<(iters + 255) / 256, 256, 0, st>>>(iters, c * 32, 1, 0, 1, eps_acc, vv, d_eps);
+                }
+                CY2P_CUDA(cudaGetLastError());
+                return CY2P_OK;
+            }
+        }
+        // (b) one cooperative launch, grid barrier per update
         if (d_eps) CY2P_CUDA(cudaMemsetAsync(eps_acc, 0, sizeof(double) * 2 * (size_t)iters, st));
         int per_sm = 0;
         CY2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_b1_persistent<T>, 256, 0));
@@ -375,11 +652,7 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
         const int need = (n + 7) / 8;
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
-        T *last = d_Xfinal ? d_Xfinal : bufB;
         double *acc = d_eps ? eps_acc : nullptr;
-        int32_t n_ = n, iters_ = iters;
-        const int32_t *tp = plan->d_t_indptr;
-        const Pair *pp = plan->d_t_pairs;
         void *args[] = {&n_, &tp, &pp, (void *)&d_X0, &d_history, &bufA, &bufB, &last, &iters_, (void *)&d_stationary, &acc};
         count_launch();
         CY2P_CUDA(cudaLaunchCooperativeKernel((void *)spmv_b1_persistent<T>, dim3(grid), dim3(256), args, 0, st));
