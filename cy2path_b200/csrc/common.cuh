@@ -37,13 +37,6 @@ struct __align__(8) Pair {
     float val;
 };
 
-// Row blocks of the TMA-staged propagation kernel: a block is a run of consecutive (permuted)
-// destination rows whose union of source cells fits the shared-memory stage.
-struct RowBlock {
-    int32_t row_begin, row_end;  // destination rows [begin, end) in plan order
-    int32_t src_begin, src_end;  // range into plan->d_block_src (unique sources of the block)
-};
-
 }  // namespace cy2p
 
 struct cy2p_plan {
@@ -64,11 +57,16 @@ struct cy2p_plan {
     // T^T: destination-major CSR, sources ascending inside a row (scipy csc_matvec's add order)
     int32_t *d_t_indptr = nullptr;
     cy2p::Pair *d_t_pairs = nullptr;
-    // staged kernel structures (built lazily by propagate_staged.cu)
-    int32_t num_blocks = 0;
-    cy2p::RowBlock *d_blocks = nullptr;
-    int32_t *d_block_src = nullptr;   // concatenated unique-source lists
-    cy2p::Pair *d_local_pairs = nullptr;  // d_t_pairs with src replaced by the slot in the block's stage
-    int32_t *d_perm = nullptr;        // plan order -> original cell id (nullptr = identity)
-    int32_t *d_iperm = nullptr;
+    // Locality ordering (built lazily by reorder.cu for batched propagation): destinations in Cuthill-McKee
+    // order so that the rows a CTA gathers lie in a narrow window of the permuted iterate (L2 hits instead of HBM)
+    int32_t reorder_state = 0;             // 0 = not tried, 1 = active, -1 = rejected (no gain) / disabled
+    int32_t *d_order = nullptr;            // [n] original cell id of permuted position q
+    int32_t *d_r_indptr = nullptr;         // [n+1] T^T row pointers in permuted destination order
+    cy2p::Pair *d_r_pairs_pp = nullptr;    // sources as permuted positions  (permuted iterate -> permuted iterate)
+    cy2p::Pair *d_r_pairs_op = nullptr;    // sources as original ids        (original iterate -> permuted iterate)
+    double span_identity = 0.0, span_reordered = 0.0;  // mean |pos(i) - pos(j)| over the stored entries
 };
+
+namespace cy2p {
+int32_t ensure_reordered(cy2p_plan *plan, cudaStream_t st);  // reorder.cu
+}

@@ -151,11 +151,10 @@ static void plan_free(cy2p_plan *p) {
     cudaFree(p->d_data);
     cudaFree(p->d_t_indptr);
     cudaFree(p->d_t_pairs);
-    cudaFree(p->d_blocks);
-    cudaFree(p->d_block_src);
-    cudaFree(p->d_local_pairs);
-    cudaFree(p->d_perm);
-    cudaFree(p->d_iperm);
+    cudaFree(p->d_order);
+    cudaFree(p->d_r_indptr);
+    cudaFree(p->d_r_pairs_pp);
+    cudaFree(p->d_r_pairs_op);
     delete p;
 }
 
@@ -338,7 +337,7 @@ int32_t cy2p_plan_info(const cy2p_plan *plan, int64_t info[8]) {
     info[3] = plan->max_out_deg;
     info[4] = plan->W;
     info[5] = plan->device;
-    info[6] = plan->num_blocks;
+    info[6] = plan->reorder_state;
     info[7] = (int64_t)plan->bytes_owned;
     return CY2P_OK;
 }

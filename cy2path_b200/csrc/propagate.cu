@@ -79,6 +79,8 @@ struct Vec<double, 1> {
     static __device__ __forceinline__ double get(const V &v, int) { return v; }
 };
 
+// dest_ids (may be null): original cell id of destination row r when the rows are in the plan's locality order
+// (reorder.cu); it indexes the stationary vector and, if out_orig is set, the output row (permuted -> original).
 // One update for destination rows [row_begin,row_end) and `ncols` columns starting at the column the
 // base pointers address. eps_acc (may be null): [kEpsCopies][ncols][2] doubles, (x.pi, x.x) partial sums of
 // this update; CTA b adds into copy b % kEpsCopies and eps_finalize_tile sums the copies.
@@ -86,8 +88,9 @@ struct Vec<double, 1> {
 template <typename T, int VEC, bool EPS>
 __global__ void __launch_bounds__(kWarps * 32, sizeof(T) == 4 ? 6 : 3)
 spmm_gather(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, const int32_t *__restrict__ t_indptr,
-            const Pair *__restrict__ pairs, const T *__restrict__ Xin, uint32_t ld_in, T *__restrict__ Xout,
-            uint32_t ld_out, int32_t ncols, const double *__restrict__ stationary, double *__restrict__ eps_acc) {
+            const Pair *__restrict__ pairs, const int32_t *__restrict__ dest_ids, int32_t out_orig,
+            const T *__restrict__ Xin, uint32_t ld_in, T *__restrict__ Xout, uint32_t ld_out, int32_t ncols,
+            const double *__restrict__ stationary, double *__restrict__ eps_acc) {
     using VT = Vec<T, VEC>;
     using V = typename VT::V;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,9 +140,10 @@ spmm_gather(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, const int3
                 const Pair e = pairs[p];
                 VT::fma(acc, e.val, VT::load(xin + (uint64_t)(uint32_t)e.src * ld_in));
             }
-            VT::store(Xout + (uint64_t)(uint32_t)r * ld_out + col, acc);
+            const int32_t cell = dest_ids ? __ldg(dest_ids + r) : r;
+            VT::store(Xout + (uint64_t)(uint32_t)(out_orig ? cell : r) * ld_out + col, acc);
             if (EPS) {
-                const T pi = (T)stationary[r];
+                const T pi = (T)stationary[cell];
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
                     const T y = (T)VT::get(acc, k);
@@ -461,8 +465,17 @@ static WsLayout ws_layout(const cy2p_plan *plan, int32_t B, int32_t iters, size_
     return w;
 }
 
+// Which T^T the update walks: the caller's order (identity) or the plan's locality order, with sources addressed in
+// the original or the permuted iterate.
+struct GatherOperand {
+    const int32_t *indptr;
+    const Pair *pairs;
+    const int32_t *dest_ids;  // null for the identity order
+    int32_t out_orig;
+};
+
 template <typename T, int VEC>
-static void launch_gather(const cy2p_plan *plan, int32_t row_begin, int32_t row_end, const T *in, uint32_t ld_in,
+static void launch_gather(const GatherOperand &g, int32_t row_begin, int32_t row_end, const T *in, uint32_t ld_in,
                           T *out, uint32_t ld_out, int32_t ncols, const double *stationary, double *eps_acc,
                           cudaStream_t st) {
     static const int rows_per_cta = [] {
@@ -473,12 +486,12 @@ static void launch_gather(const cy2p_plan *plan, int32_t row_begin, int32_t row_
               (unsigned)((ncols + 32 * VEC - 1) / (32 * VEC)));
     count_launch();
     if (eps_acc)
-        spmm_gather<T, VEC, true><<<grid, kWarps * 32, 0, st>>>(row_begin, row_end, rows_per_cta, plan->d_t_indptr,
-                                                               plan->d_t_pairs, in, ld_in, out, ld_out, ncols,
+        spmm_gather<T, VEC, true><<<grid, kWarps * 32, 0, st>>>(row_begin, row_end, rows_per_cta, g.indptr, g.pairs,
+                                                               g.dest_ids, g.out_orig, in, ld_in, out, ld_out, ncols,
                                                                stationary, eps_acc);
     else
-        spmm_gather<T, VEC, false><<<grid, kWarps * 32, 0, st>>>(row_begin, row_end, rows_per_cta, plan->d_t_indptr,
-                                                                plan->d_t_pairs, in, ld_in, out, ld_out, ncols,
+        spmm_gather<T, VEC, false><<<grid, kWarps * 32, 0, st>>>(row_begin, row_end, rows_per_cta, g.indptr, g.pairs,
+                                                                g.dest_ids, g.out_orig, in, ld_in, out, ld_out, ncols,
                                                                 nullptr, nullptr);
 }
 
@@ -668,15 +681,24 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
     const bool wide = (B % VW == 0) && aligned16(d_X0) && (!d_Xfinal || aligned16(d_Xfinal)) &&
                       (!d_history || aligned16(d_history));
     const int64_t slots = d_history ? ((int64_t)iters + history_stride - 1) / history_stride : 0;
+    // locality ordering: worth building when the work amortises the one-off host pass
+    if (plan->reorder_state == 0 && (int64_t)B * iters >= 4096 && B >= 32) {
+        const int32_t rc = ensure_reordered(plan, st);
+        if (rc != CY2P_OK) return rc;
+    }
+    const bool reord = plan->reorder_state == 1;
+    const GatherOperand ident = {plan->d_t_indptr, plan->d_t_pairs, nullptr, 0};
     for (int32_t c0 = 0; c0 < B; c0 += w.tile) {
         const int32_t nc = (B - c0 < w.tile) ? B - c0 : w.tile;
         if (d_eps)
             CY2P_CUDA(cudaMemsetAsync(eps_acc, 0, sizeof(double) * 2 * (size_t)iters * (size_t)nc * kEpsCopies, st));
         const T *src = d_history ? d_history + c0 : d_X0 + c0;  // history row 0 holds x0
         uint32_t ld_src = (uint32_t)B;
+        bool src_perm = false;  // caller-visible buffers are in the caller's cell order, the scratch in plan order
         for (int32_t it = 0; it < iters; ++it) {
             T *dst;
             uint32_t ld_dst;
+            bool dst_perm = false;
             const int64_t nxt = (int64_t)it + 1;
             if (d_history && nxt % history_stride == 0 && nxt / history_stride < slots) {
                 dst = d_history + (size_t)(nxt / history_stride) * (size_t)n * B + c0;
@@ -687,14 +709,23 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
             } else {
                 dst = (src == bufA) ? bufB : bufA;
                 ld_dst = (uint32_t)nc;
+                dst_perm = reord;
             }
             double *acc = d_eps ? eps_acc + 2 * (size_t)it * (size_t)nc * kEpsCopies : nullptr;
+            GatherOperand g = ident;
+            if (reord) {
+                g.indptr = plan->d_r_indptr;
+                g.pairs = src_perm ? plan->d_r_pairs_pp : plan->d_r_pairs_op;
+                g.dest_ids = plan->d_order;
+                g.out_orig = dst_perm ? 0 : 1;
+            }
             if (wide && (nc % VW == 0))
-                launch_gather<T, VW>(plan, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st);
+                launch_gather<T, VW>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st);
             else
-                launch_gather<T, 1>(plan, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st);
+                launch_gather<T, 1>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st);
             src = dst;
             ld_src = ld_dst;
+            src_perm = dst_perm;
         }
         if (d_Xfinal && src != d_Xfinal + c0)  // the last iterate landed in a history slot / scratch
             CY2P_CUDA(cudaMemcpy2DAsync(d_Xfinal + c0, sizeof(T) * (size_t)B, src, sizeof(T) * (size_t)ld_src,
@@ -719,10 +750,11 @@ static int32_t propagate_rows_impl(cy2p_plan *plan, const T *d_X, T *d_Y, int32_
     cudaStream_t st = (cudaStream_t)stream;
     CY2P_CUDA(cudaSetDevice(plan->device));
     if (row_begin == row_end) return CY2P_OK;
+    const GatherOperand ident = {plan->d_t_indptr, plan->d_t_pairs, nullptr, 0};
     if (B % VW == 0 && aligned16(d_X) && aligned16(d_Y))
-        launch_gather<T, VW>(plan, row_begin, row_end, d_X, B, d_Y, B, B, nullptr, nullptr, st);
+        launch_gather<T, VW>(ident, row_begin, row_end, d_X, B, d_Y, B, B, nullptr, nullptr, st);
     else
-        launch_gather<T, 1>(plan, row_begin, row_end, d_X, B, d_Y, B, B, nullptr, nullptr, st);
+        launch_gather<T, 1>(ident, row_begin, row_end, d_X, B, d_Y, B, B, nullptr, nullptr, st);
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }

@@ -60,7 +60,7 @@ int32_t cy2p_plan_create_host(int32_t n, int64_t nnz, const int32_t *h_indptr, c
                               const float *h_data, int32_t device, void *stream, cy2p_plan **out);
 int32_t cy2p_plan_destroy(cy2p_plan *plan);
 /* info[0]=n info[1]=nnz info[2]=max in-degree info[3]=max out-degree (stored) info[4]=CDF table width W
- * info[5]=device info[6]=number of row blocks of the staged kernel info[7]=bytes of device memory owned */
+ * info[5]=device info[6]=locality ordering (0 not built yet, 1 active, -1 rejected) info[7]=bytes of device memory owned */
 int32_t cy2p_plan_info(const cy2p_plan *plan, int64_t info[8]);
 
 /* ---- K1: MSM state-probability propagation  X <- X . T, `iters` times ----------------------

@@ -129,6 +129,57 @@ def test_long_run_precision_fp32_vs_fp64_iterate():
     _assert_close(r32s, ref60)
 
 
+def test_locality_ordering_path_matches_oracle():
+    """Batched runs long enough to amortise it switch to the plan's Cuthill-McKee cell order (reorder.cu): the
+    first update reads the caller's order, the middle ones run permuted -> permuted, history slots and the final
+    iterate are written back in the caller's order."""
+    import ctypes
+
+    import torch
+
+    from cy2path_b200 import _lib
+    from cy2path_b200.synth import batched_starts, knn_velocity_tpm
+
+    g = knn_velocity_tpm(2000, k=12, seed=21)
+    T = g["T"]
+    plan = _lib.Plan(T)
+    info = (ctypes.c_int64 * 8)()
+    X0 = batched_starts(T, 64, seed=9)
+    stat = g["end_points"] / g["end_points"].sum()
+    iters = 70
+    out = _lib.propagate(plan, torch.from_numpy(X0).cuda(), iters, stationary=stat, want_eps=True, history_stride=16)
+    _lib.check(_lib.load().cy2p_plan_info(plan.handle, info))
+    assert info[6] == 1, "the synthetic cell order is random: the ordering must have been accepted"
+    ref = np.asarray(X0, dtype=np.float64)
+    eps_ref = np.empty((iters, 64))
+    hist_ref = []
+    for it in range(iters):
+        if it % 16 == 0:
+            hist_ref.append(ref.copy())
+        ref = ofast.propagate_batch(T, ref, 1)
+        eps_ref[it] = [omsm.cosine_distance(ref[:, b], stat) for b in range(64)]
+    h = out["history"].cpu().numpy()
+    assert h.shape == (len(hist_ref), 2000, 64)
+    for a, b in zip(h, hist_ref):
+        assert np.abs(a - b).max() <= MAX_ABS and omsm.rel_l1(a, b) <= 3e-6  # 64 iterations of fp32 rounding
+    _assert_close(h[0], hist_ref[0])
+    got = out["final"].cpu().numpy()
+    assert np.abs(got - ref).max() <= MAX_ABS and omsm.rel_l1(got, ref) <= 3e-6
+    assert np.abs(out["eps"].cpu().numpy() - eps_ref).max() <= 1e-6
+    # same answer (to fp32 summation order) as the caller-order path of a fresh plan with the ordering disabled
+    import os
+
+    os.environ["CY2P_REORDER"] = "0"
+    try:
+        plan2 = _lib.Plan(T)
+        out2 = _lib.propagate(plan2, torch.from_numpy(X0).cuda(), iters)
+        _lib.check(_lib.load().cy2p_plan_info(plan2.handle, info))
+        assert info[6] == -1
+    finally:
+        del os.environ["CY2P_REORDER"]
+    assert np.abs(out2["final"].cpu().numpy() - got).max() <= 1e-6
+
+
 def test_history_stride_and_linearity():
     import torch
 
