@@ -136,10 +136,23 @@ __global__ void cdf_build_kernel(int32_t n, int32_t W, const int32_t *__restrict
     }
 }
 
+// Temporaries come from the device's stream-ordered pool (cudaMallocAsync): plan creation sits inside the timed
+// end-to-end path of the small single-start case, and cudaMalloc/cudaFree cost ~0.1-0.5 ms each.
+static void keep_pool_cached(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[device] = true;
+}
+
 template <typename T>
-static int32_t dmalloc(cy2p_plan *plan, T **ptr, size_t count) {
+static int32_t dmalloc(cy2p_plan *plan, T **ptr, size_t count, cudaStream_t st) {
     size_t bytes = sizeof(T) * (count ? count : 1);
-    CY2P_CUDA(cudaMalloc((void **)ptr, bytes));
+    CY2P_CUDA(cudaMallocAsync((void **)ptr, bytes, st));
     plan->bytes_owned += bytes;
     return CY2P_OK;
 }
@@ -193,11 +206,12 @@ static int32_t plan_build(int32_t n, int64_t nnz, const int32_t *indptr, const i
         }                                                                                           \
     } while (0)
 
-    TRY(dmalloc(plan, &plan->d_indptr, (size_t)n + 1));
-    TRY(dmalloc(plan, &plan->d_indices, (size_t)nnz));
-    TRY(dmalloc(plan, &plan->d_data, (size_t)nnz));
-    TRY(dmalloc(plan, &plan->d_t_indptr, (size_t)n + 1));
-    TRY(dmalloc(plan, &plan->d_t_pairs, (size_t)nnz));
+    keep_pool_cached(device);
+    TRY(dmalloc(plan, &plan->d_indptr, (size_t)n + 1, st));
+    TRY(dmalloc(plan, &plan->d_indices, (size_t)nnz, st));
+    TRY(dmalloc(plan, &plan->d_data, (size_t)nnz, st));
+    TRY(dmalloc(plan, &plan->d_t_indptr, (size_t)n + 1, st));
+    TRY(dmalloc(plan, &plan->d_t_pairs, (size_t)nnz, st));
     TRY_CUDA(cudaMemcpyAsync(plan->d_indptr, indptr, sizeof(int32_t) * ((size_t)n + 1), kind, st));
     if (nnz) {
         TRY_CUDA(cudaMemcpyAsync(plan->d_indices, indices, sizeof(int32_t) * (size_t)nnz, kind, st));
@@ -209,13 +223,13 @@ static int32_t plan_build(int32_t n, int64_t nnz, const int32_t *indptr, const i
             *key_out = nullptr;
     void *cub_tmp = nullptr;
     auto free_tmp = [&]() {
-        cudaFree(flags);
-        cudaFree(indeg);
-        cudaFree(rowid);
-        cudaFree(ord_in);
-        cudaFree(ord_out);
-        cudaFree(key_out);
-        cudaFree(cub_tmp);
+        cudaFreeAsync(flags, st);
+        cudaFreeAsync(indeg, st);
+        cudaFreeAsync(rowid, st);
+        cudaFreeAsync(ord_in, st);
+        cudaFreeAsync(ord_out, st);
+        cudaFreeAsync(key_out, st);
+        cudaFreeAsync(cub_tmp, st);
     };
 #define TRY_CUDA_T(call)                                                                            \
     do {                                                                                            \
@@ -228,13 +242,14 @@ static int32_t plan_build(int32_t n, int64_t nnz, const int32_t *indptr, const i
         }                                                                                           \
     } while (0)
 
+    keep_pool_cached(device);
     const size_t nz1 = (size_t)(nnz ? nnz : 1);
-    TRY_CUDA_T(cudaMalloc((void **)&flags, sizeof(int32_t) * 8));
-    TRY_CUDA_T(cudaMalloc((void **)&indeg, sizeof(int32_t) * ((size_t)n + 1)));
-    TRY_CUDA_T(cudaMalloc((void **)&rowid, sizeof(int32_t) * nz1));
-    TRY_CUDA_T(cudaMalloc((void **)&ord_in, sizeof(int32_t) * nz1));
-    TRY_CUDA_T(cudaMalloc((void **)&ord_out, sizeof(int32_t) * nz1));
-    TRY_CUDA_T(cudaMalloc((void **)&key_out, sizeof(int32_t) * nz1));
+    TRY_CUDA_T(cudaMallocAsync((void **)&flags, sizeof(int32_t) * 8, st));
+    TRY_CUDA_T(cudaMallocAsync((void **)&indeg, sizeof(int32_t) * ((size_t)n + 1), st));
+    TRY_CUDA_T(cudaMallocAsync((void **)&rowid, sizeof(int32_t) * nz1, st));
+    TRY_CUDA_T(cudaMallocAsync((void **)&ord_in, sizeof(int32_t) * nz1, st));
+    TRY_CUDA_T(cudaMallocAsync((void **)&ord_out, sizeof(int32_t) * nz1, st));
+    TRY_CUDA_T(cudaMallocAsync((void **)&key_out, sizeof(int32_t) * nz1, st));
     TRY_CUDA_T(cudaMemsetAsync(flags, 0, sizeof(int32_t) * 8, st));
     TRY_CUDA_T(cudaMemsetAsync(indeg, 0, sizeof(int32_t) * ((size_t)n + 1), st));
 
@@ -274,7 +289,7 @@ static int32_t plan_build(int32_t n, int64_t nnz, const int32_t *indptr, const i
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, plan->d_indices, key_out, ord_in, ord_out, (int)nnz, 0,
                                     end_bit, st);
     size_t tmp_bytes = tmp_scan > tmp_sort ? tmp_scan : tmp_sort;
-    TRY_CUDA_T(cudaMalloc(&cub_tmp, tmp_bytes ? tmp_bytes : 1));
+    TRY_CUDA_T(cudaMallocAsync(&cub_tmp, tmp_bytes ? tmp_bytes : 1, st));
     TRY_CUDA_T(cub::DeviceScan::ExclusiveSum(cub_tmp, tmp_scan, indeg, plan->d_t_indptr, n + 1, st));
     if (nnz) {
         count_launch();

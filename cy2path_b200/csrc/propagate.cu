@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(kWarps * 32, sizeof(T) == 4 ? 6 : 3)
 spmm_gather(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, const int32_t *__restrict__ t_indptr,
             const Pair *__restrict__ pairs, const int32_t *__restrict__ dest_ids, int32_t out_orig,
             const T *__restrict__ Xin, uint32_t ld_in, T *__restrict__ Xout, uint32_t ld_out, int32_t ncols,
-            const double *__restrict__ stationary, double *__restrict__ eps_acc) {
+            const double *__restrict__ stationary, double *__restrict__ eps_acc, T *const *__restrict__ peer_out,
+            int32_t npeers) {
     using VT = Vec<T, VEC>;
     using V = typename VT::V;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,7 +142,14 @@ spmm_gather(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, const int3
                 VT::fma(acc, e.val, VT::load(xin + (uint64_t)(uint32_t)e.src * ld_in));
             }
             const int32_t cell = dest_ids ? __ldg(dest_ids + r) : r;
-            VT::store(Xout + (uint64_t)(uint32_t)(out_orig ? cell : r) * ld_out + col, acc);
+            const uint64_t off = (uint64_t)(uint32_t)(out_orig ? cell : r) * ld_out + col;
+            if (peer_out == nullptr) {
+                VT::store(Xout + off, acc);
+            } else {
+                // fused all-gather (row-partitioned propagation): the finished row goes straight into every rank's
+                // next-iterate buffer — local HBM for this rank, NVLink peer stores for the others
+                for (int32_t g = 0; g < npeers; ++g) VT::store(peer_out[g] + off, acc);
+            }
             if (EPS) {
                 const T pi = (T)stationary[cell];
 #pragma unroll
@@ -397,6 +405,42 @@ spmv_b1_cluster_dsmem(int32_t n, const int32_t *__restrict__ t_indptr, const Pai
     }
 }
 
+// B == 1 update of a row range (row-partitioned propagation, config 5): 8 lanes per destination row, four gathers in
+// flight per lane, 3 shuffle steps. The general kernel would leave 31 of 32 lanes idle at B == 1.
+template <typename T>
+__global__ void __launch_bounds__(256)
+spmv_rows(int32_t row_begin, int32_t row_end, const int32_t *__restrict__ t_indptr, const Pair *__restrict__ pairs,
+          const T *__restrict__ x, T *__restrict__ y, T *const *__restrict__ peer_out, int32_t npeers) {
+    constexpr int G = 8;
+    const int lane = threadIdx.x & 31, gl = lane % G;
+    const int32_t r = row_begin + (int32_t)((blockIdx.x * (blockDim.x / G)) + threadIdx.x / G);
+    const bool ok = r < row_end;
+    const int32_t beg = ok ? t_indptr[r] : 0, end = ok ? t_indptr[r + 1] : 0;
+    T acc = (T)0;
+    for (int32_t p0 = beg + gl; p0 < end; p0 += 4 * G) {
+        Pair e[4];
+        T xv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int32_t p = p0 + k * G;
+            e[k] = p < end ? pairs[p] : Pair{0, 0.f};
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xv[k] = (p0 + k * G < end) ? __ldg(x + e[k].src) : (T)0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc = fma((T)e[k].val, xv[k], acc);
+    }
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (ok) {
+        if (peer_out == nullptr) {
+            if (gl == 0) y[r] = acc;
+        } else {  // every lane of the group holds the sum: lane gl serves peers gl, gl + G, ...
+            for (int32_t g = gl; g < npeers; g += G) peer_out[g][r] = acc;
+        }
+    }
+}
+
 __global__ void sumsq_kernel(int32_t n, const double *__restrict__ v, double *out) {
     double s = 0.0;
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s = fma(v[i], v[i], s);
@@ -472,6 +516,8 @@ struct GatherOperand {
     const Pair *pairs;
     const int32_t *dest_ids;  // null for the identity order
     int32_t out_orig;
+    void *const *peer_out = nullptr;  // device array of `npeers` output base pointers (fused all-gather), or null
+    int32_t npeers = 0;
 };
 
 template <typename T, int VEC>
@@ -488,11 +534,11 @@ static void launch_gather(const GatherOperand &g, int32_t row_begin, int32_t row
     if (eps_acc)
         spmm_gather<T, VEC, true><<<grid, kWarps * 32, 0, st>>>(row_begin, row_end, rows_per_cta, g.indptr, g.pairs,
                                                                g.dest_ids, g.out_orig, in, ld_in, out, ld_out, ncols,
-                                                               stationary, eps_acc);
+                                                               stationary, eps_acc, (T *const *)g.peer_out, g.npeers);
     else
         spmm_gather<T, VEC, false><<<grid, kWarps * 32, 0, st>>>(row_begin, row_end, rows_per_cta, g.indptr, g.pairs,
                                                                 g.dest_ids, g.out_orig, in, ld_in, out, ld_out, ncols,
-                                                                nullptr, nullptr);
+                                                                nullptr, nullptr, (T *const *)g.peer_out, g.npeers);
 }
 
 template <typename T>
@@ -751,7 +797,12 @@ static int32_t propagate_rows_impl(cy2p_plan *plan, const T *d_X, T *d_Y, int32_
     CY2P_CUDA(cudaSetDevice(plan->device));
     if (row_begin == row_end) return CY2P_OK;
     const GatherOperand ident = {plan->d_t_indptr, plan->d_t_pairs, nullptr, 0};
-    if (B % VW == 0 && aligned16(d_X) && aligned16(d_Y))
+    if (B == 1) {
+        const int rows_per_cta = 256 / 8;
+        count_launch();
+        spmv_rows<T><<<(unsigned)((row_end - row_begin + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(
+            row_begin, row_end, plan->d_t_indptr, plan->d_t_pairs, d_X, d_Y, nullptr, 0);
+    } else if (B % VW == 0 && aligned16(d_X) && aligned16(d_Y))
         launch_gather<T, VW>(ident, row_begin, row_end, d_X, B, d_Y, B, B, nullptr, nullptr, st);
     else
         launch_gather<T, 1>(ident, row_begin, row_end, d_X, B, d_Y, B, B, nullptr, nullptr, st);
@@ -759,11 +810,104 @@ static int32_t propagate_rows_impl(cy2p_plan *plan, const T *d_X, T *d_Y, int32_
     return CY2P_OK;
 }
 
+// Row range of one update entirely in the plan's locality order (X and Y permuted): the row-partitioned driver
+// permutes the start distribution once, iterates here, and un-permutes the result once.
+template <typename T>
+static int32_t propagate_rows_ordered_impl(cy2p_plan *plan, const T *d_Xp, T *d_Yp, int32_t B, int32_t q_begin,
+                                           int32_t q_end, void *stream, void *const *d_peer_out = nullptr,
+                                           int32_t npeers = 0) {
+    constexpr int VW = Wide<T>::VEC;
+    CY2P_REQUIRE(plan && d_Xp && (d_Yp || d_peer_out), "null pointer");
+    CY2P_REQUIRE(!d_peer_out || (npeers >= 1 && npeers <= 64), "1 <= npeers <= 64 required with peer outputs");
+    CY2P_REQUIRE(B >= 1 && q_begin >= 0 && q_end <= plan->n && q_begin <= q_end, "bad row range / B");
+    cudaStream_t st = (cudaStream_t)stream;
+    CY2P_CUDA(cudaSetDevice(plan->device));
+    if (q_begin == q_end) return CY2P_OK;
+    const bool reord = plan->reorder_state == 1;
+    const int32_t *ip = reord ? plan->d_r_indptr : plan->d_t_indptr;
+    const Pair *pr = reord ? plan->d_r_pairs_pp : plan->d_t_pairs;
+    if (B == 1) {
+        const int rows_per_cta = 256 / 8;
+        count_launch();
+        spmv_rows<T><<<(unsigned)((q_end - q_begin + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(
+            q_begin, q_end, ip, pr, d_Xp, d_Yp, (T *const *)d_peer_out, npeers);
+    } else {
+        GatherOperand g = {ip, pr, nullptr, 0};  // rows stay in plan order on both sides
+        g.peer_out = d_peer_out;
+        g.npeers = npeers;
+        if (B % VW == 0 && aligned16(d_Xp) && aligned16(d_Yp))
+            launch_gather<T, VW>(g, q_begin, q_end, d_Xp, B, d_Yp, B, B, nullptr, nullptr, st);
+        else
+            launch_gather<T, 1>(g, q_begin, q_end, d_Xp, B, d_Yp, B, B, nullptr, nullptr, st);
+    }
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+__global__ void iota_kernel(int32_t n, int32_t *out) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
 }  // namespace cy2p
 
 using namespace cy2p;
 
 extern "C" {
+
+int32_t cy2p_plan_order(cy2p_plan *plan, int32_t *d_order, void *stream) {
+    CY2P_REQUIRE(plan && d_order, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CY2P_CUDA(cudaSetDevice(plan->device));
+    const int32_t rc = ensure_reordered(plan, st);
+    if (rc != CY2P_OK) return rc;
+    if (plan->reorder_state == 1) {
+        CY2P_CUDA(cudaMemcpyAsync(d_order, plan->d_order, sizeof(int32_t) * (size_t)plan->n, cudaMemcpyDeviceToDevice, st));
+    } else {
+        count_launch();
+        iota_kernel<<<(plan->n + 255) / 256, 256, 0, st>>>(plan->n, d_order);
+    }
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+int32_t cy2p_propagate_rows_ordered(cy2p_plan *plan, const float *d_Xp, float *d_Yp, int32_t B, int32_t q_begin,
+                                    int32_t q_end, void *stream) {
+    return propagate_rows_ordered_impl<float>(plan, d_Xp, d_Yp, B, q_begin, q_end, stream);
+}
+
+int32_t cy2p_propagate_rows_ordered_f64(cy2p_plan *plan, const double *d_Xp, double *d_Yp, int32_t B, int32_t q_begin,
+                                        int32_t q_end, void *stream) {
+    return propagate_rows_ordered_impl<double>(plan, d_Xp, d_Yp, B, q_begin, q_end, stream);
+}
+
+int32_t cy2p_propagate_rows_allgather(cy2p_plan *plan, const float *d_Xp, void *const *d_peer_out, int32_t npeers,
+                                      int32_t B, int32_t q_begin, int32_t q_end, void *stream) {
+    return propagate_rows_ordered_impl<float>(plan, d_Xp, nullptr, B, q_begin, q_end, stream, d_peer_out, npeers);
+}
+
+int32_t cy2p_propagate_rows_allgather_f64(cy2p_plan *plan, const double *d_Xp, void *const *d_peer_out,
+                                          int32_t npeers, int32_t B, int32_t q_begin, int32_t q_end, void *stream) {
+    return propagate_rows_ordered_impl<double>(plan, d_Xp, nullptr, B, q_begin, q_end, stream, d_peer_out, npeers);
+}
+
+int32_t cy2p_enable_peer_access(int32_t device, int32_t peer) {
+    CY2P_CUDA(cudaSetDevice(device));
+    if (device == peer) return CY2P_OK;
+    int can = 0;
+    CY2P_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) {
+        set_error("device %d cannot access peer %d", device, peer);
+        return CY2P_ERR_CUDA;
+    }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", device, peer, cudaGetErrorString(e));
+        return CY2P_ERR_CUDA;
+    }
+    cudaGetLastError();
+    return CY2P_OK;
+}
 
 size_t cy2p_propagate_ws_bytes(const cy2p_plan *plan, int32_t B, int32_t iters) {
     if (!plan || B < 1 || iters < 0) return 0;

@@ -85,6 +85,111 @@ def _cuda_update_rows(plan):
     return update
 
 
+def plan_order(plan):
+    """Device int64 tensor: original cell id at each position of the plan's locality order (cy2p_plan_order)."""
+    import torch
+
+    from . import _lib
+
+    order = torch.empty(plan.n, dtype=torch.int32, device=plan.device)
+    with torch.cuda.device(plan.device):
+        _lib.check(_lib.load().cy2p_plan_order(plan.handle, _lib.ptr(order), _lib.stream_ptr(plan.device)))
+    return order.long()
+
+
+def cuda_row_update_ordered(plan):
+    """Row update with X and Y in the plan's locality order (cy2p_propagate_rows_ordered)."""
+    from . import _lib
+
+    lib = _lib.load()
+
+    def update(X, Y, r0, r1):
+        fn = lib.cy2p_propagate_rows_ordered_f64 if X.dtype.itemsize == 8 else lib.cy2p_propagate_rows_ordered
+        _lib.check(fn(plan.handle, _lib.ptr(X), _lib.ptr(Y), int(X.shape[1]), int(r0), int(r1), _lib.stream_ptr(X.device)))
+
+    return update
+
+
+def propagate_row_partitioned_cuda(plan, X0, iters, group=None, ordered=True):
+    """Config-5 driver on the CUDA path: with ``ordered`` the iterate is permuted into the plan's locality order
+    once, every update runs in that order (gathers hit a narrow window of X), and the result is un-permuted once."""
+    import torch
+
+    if not ordered:
+        return propagate_row_partitioned(plan.n, X0, iters, cuda_row_update(plan), group=group)
+    order = plan_order(plan)
+    Xp = X0.index_select(0, order)
+    out_p = propagate_row_partitioned(plan.n, Xp, iters, cuda_row_update_ordered(plan), group=group)
+    out = torch.empty_like(out_p)
+    out.index_copy_(0, order, out_p)
+    return out
+
+
+def _symmetric_buffers(shape, dtype, dev, group=None):
+    """Allocate a buffer of `shape` that every rank of `group` can address from its own kernels.
+
+    Plumbing only: torch's symmetric-memory allocator (cuMem + handle exchange + peer mapping) provides the peer
+    pointers and a device-side cross-rank barrier; the data path is cy2p_propagate_rows_allgather's stores.
+    Returns (local tensor, [base pointer on rank r as seen from this rank], barrier callable)."""
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm
+
+    world, rank = _world(group)
+    if world == 1:
+        t = torch.zeros(shape, dtype=dtype, device=dev)
+        return t, [t.data_ptr()], (lambda: None)
+    t = symm.empty(shape, dtype=dtype, device=dev)
+    hdl = symm.rendezvous(t, group=group if group is not None else dist.group.WORLD)
+    t.zero_()
+    ptrs = [int(p) for p in hdl.buffer_ptrs]
+    import os
+
+    if os.environ.get("CY2P_FUSED_BARRIER", "nccl") == "symm":
+        return t, ptrs, (lambda: hdl.barrier(channel=0))
+    # stream-ordered cross-rank barrier: a one-element NCCL all-reduce (a rank leaves it only after every rank's
+    # preceding kernel, i.e. its peer stores, has completed)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    return t, ptrs, (lambda: dist.all_reduce(flag, group=group))
+
+
+def propagate_row_partitioned_fused(plan, X0, iters, group=None):
+    """Config-5 driver with the exchange fused into the update: every rank's kernel stores its finished rows
+    straight into ALL ranks' next-iterate buffers (own HBM + NVLink peer stores, cy2p_propagate_rows_allgather),
+    so no separate all-gather follows the gather; ranks only meet at a device-side barrier that orders the
+    ping-pong buffers. The iterate stays in the plan's locality order throughout."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+
+    lib = _lib.load()
+    world, rank = _world(group)
+    n, B = plan.n, int(X0.shape[1])
+    dev = X0.device
+    order = plan_order(plan)
+    m, blocks = row_blocks(n, world)
+    with torch.cuda.device(dev):
+        buf, ptrs, barrier = _symmetric_buffers((2, n, B), X0.dtype, dev, group)
+        half = n * B * X0.element_size()
+        ptr_arrays = [torch.tensor([p + k * half for p in ptrs], dtype=torch.int64, device=dev) for k in range(2)]
+        buf[0].copy_(X0.index_select(0, order))
+        fn = lib.cy2p_propagate_rows_allgather_f64 if X0.dtype.itemsize == 8 else lib.cy2p_propagate_rows_allgather
+        r0, r1 = blocks[rank]
+        barrier()  # every rank has mapped its peers and filled buffer 0
+        for it in range(int(iters)):
+            cur, nxt = it & 1, (it + 1) & 1
+            _lib.check(fn(plan.handle, _lib.ptr(buf[cur]), ctypes.c_void_p(ptr_arrays[nxt].data_ptr()), world, B,
+                          int(r0), int(r1), _lib.stream_ptr(dev)))
+            barrier()  # all ranks' stores into buffer `nxt` have landed; buffer `cur` may be overwritten next
+        out_p = buf[int(iters) & 1]
+        out = torch.empty_like(out_p)
+        out.index_copy_(0, order, out_p)
+        barrier()  # nobody releases its buffers while a peer may still be writing
+    return out
+
+
 def propagate_row_partitioned(n, X0, iters, update_rows, group=None, history_every=0):
     """Row-partitioned propagation (BASELINE config 5).
 

@@ -100,6 +100,27 @@ int32_t cy2p_propagate_rows(cy2p_plan *plan, const float *d_X, float *d_Y, int32
 int32_t cy2p_propagate_rows_f64(cy2p_plan *plan, const double *d_X, double *d_Y, int32_t B,
                                 int32_t row_begin, int32_t row_end, void *stream);
 
+/* Locality order of the plan (reorder.cu): d_order[q] = original cell id at position q of the plan's Cuthill-McKee
+ * order (identity if the ordering was rejected because the input is already well ordered). Builds the ordering
+ * on first use (host pass, synchronises `stream`). The *_ordered row update takes X and Y already in that order,
+ * so a row-partitioned run permutes the start distributions once and un-permutes the result once. */
+int32_t cy2p_plan_order(cy2p_plan *plan, int32_t *d_order, void *stream);
+int32_t cy2p_propagate_rows_ordered(cy2p_plan *plan, const float *d_Xp, float *d_Yp, int32_t B,
+                                    int32_t q_begin, int32_t q_end, void *stream);
+int32_t cy2p_propagate_rows_ordered_f64(cy2p_plan *plan, const double *d_Xp, double *d_Yp, int32_t B,
+                                        int32_t q_begin, int32_t q_end, void *stream);
+
+/* Fused update + all-gather for the row partition: the kernel stores every finished row of [q_begin, q_end) into
+ * ALL `npeers` next-iterate buffers (d_peer_out: device array of npeers base pointers, each an [n][B] iterate in
+ * plan order; one of them is this rank's own, the others are peer-mapped over NVLink), so the exchange overlaps the
+ * gather row by row instead of following it as a separate collective. The caller provides the peer mappings
+ * (CUDA IPC) and a cross-rank barrier between updates (cy2path_b200/dist.py). */
+int32_t cy2p_propagate_rows_allgather(cy2p_plan *plan, const float *d_Xp, void *const *d_peer_out, int32_t npeers,
+                                      int32_t B, int32_t q_begin, int32_t q_end, void *stream);
+int32_t cy2p_propagate_rows_allgather_f64(cy2p_plan *plan, const double *d_Xp, void *const *d_peer_out,
+                                          int32_t npeers, int32_t B, int32_t q_begin, int32_t q_end, void *stream);
+int32_t cy2p_enable_peer_access(int32_t device, int32_t peer);
+
 /* ---- K0/K2: chain sampling ------------------------------------------------------------------
  * cy2p_cdf_build replaces extract_nonzero_entries (simulation.py:15-53): idx int32 [n][W] and
  * cum float32 [n][W] = round3(float32 sequential cumsum of the row), zero padded; W from plan_info.

@@ -233,6 +233,34 @@ def test_row_partition_equals_full_update():
             assert torch.equal(Y, full)
 
 
+def test_row_partition_in_locality_order():
+    """Config-5 driver with the iterate kept in the plan's locality order: virtual ranks == unsharded run."""
+    import torch
+
+    from cy2path_b200 import _lib
+    from cy2path_b200 import dist as c2dist
+    from cy2path_b200.synth import batched_starts, knn_velocity_tpm
+
+    g = knn_velocity_tpm(1500, k=10, seed=23)
+    plan = _lib.Plan(g["T"])
+    order = c2dist.plan_order(plan)
+    assert sorted(order.cpu().tolist()) == list(range(1500))
+    upd = c2dist.cuda_row_update_ordered(plan)
+    for B in (1, 32):
+        X = torch.from_numpy(batched_starts(g["T"], B, seed=3)).cuda()
+        ref = _lib.propagate(plan, X, 6)["final"]
+        got = c2dist.propagate_row_partitioned_cuda(plan, X, 6, ordered=True)  # world size 1
+        assert torch.allclose(got, ref, rtol=0, atol=2e-7)
+        # three virtual ranks over the permuted rows tile to the same update
+        Xp = X.index_select(0, order)
+        Yp = torch.zeros_like(Xp)
+        for r0, r1 in ((0, 400), (400, 1100), (1100, 1500)):
+            upd(Xp, Yp, r0, r1)
+        one = torch.empty_like(Yp)
+        one.index_copy_(0, order, Yp)
+        assert torch.allclose(one, _lib.propagate(plan, X, 1)["final"], rtol=0, atol=2e-7)
+
+
 def test_bad_csr_and_workspace_errors():
     import scipy.sparse as sp
 

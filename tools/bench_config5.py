@@ -15,10 +15,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--cells", dest="n", type=int, default=1_000_000)
     ap.add_argument("--B", type=int, default=1)
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--f64", type=int, default=0)
+    ap.add_argument("--ordered", type=int, default=1)
+    ap.add_argument("--fused", type=int, default=0, help="fused update + peer-store all-gather instead of NCCL")
+    ap.add_argument("--cache", default="/tmp/cy2p_config5_graph.npz", help="graph cache on the box (generated once)")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -32,21 +35,34 @@ def main():
     from cy2path_b200 import _lib, dist as c2dist
     from cy2path_b200.synth import batched_starts, knn_velocity_tpm
 
-    g = knn_velocity_tpm(a.n, seed=5)
-    T = g["T"]
+    import scipy.sparse as sp
+
+    cache = f"{a.cache}.{a.n}"
+    if rank == 0 and not os.path.exists(cache):
+        g = knn_velocity_tpm(a.n, seed=5)
+        np.savez(cache + ".tmp.npz", indptr=g["T"].indptr, indices=g["T"].indices, data=g["T"].data)
+        os.replace(cache + ".tmp.npz", cache)
+    if world > 1:
+        dist.barrier()
+    z = np.load(cache)
+    T = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(a.n, a.n))
     plan = _lib.Plan(T)
     X0 = torch.from_numpy(batched_starts(T, a.B, seed=5)).cuda()
     if a.f64:
         X0 = X0.double()
-    upd = c2dist.cuda_row_update(plan)
+    def run(iters):
+        if a.fused:
+            return c2dist.propagate_row_partitioned_fused(plan, X0, iters)
+        return c2dist.propagate_row_partitioned_cuda(plan, X0, iters, ordered=bool(a.ordered))
+
     for _ in range(2):
-        c2dist.propagate_row_partitioned(a.n, X0, 10, upd)
+        run(10)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    out = c2dist.propagate_row_partitioned(a.n, X0, a.iters, upd)
+    out = run(a.iters)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -65,7 +81,7 @@ def main():
                           "cell_iterations_per_s": a.n * a.B * a.iters / (ms * 1e-3),
                           "allgather_bytes_per_iter_per_rank": ag_bytes,
                           "allgather_GBps_if_all_time_were_comm": ag_bytes * a.iters / (ms * 1e-3) / 1e9,
-                          "mass_checksum": chk, "max_abs_vs_unsharded": err, "dtype": "f64" if a.f64 else "f32"}))
+                          "ordered": a.ordered, "fused": a.fused, "mass_checksum": chk, "max_abs_vs_unsharded": err, "dtype": "f64" if a.f64 else "f32"}))
     if world > 1:
         dist.destroy_process_group()
 
