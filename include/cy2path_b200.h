@@ -74,7 +74,8 @@ int32_t cy2p_plan_info(const cy2p_plan *plan, int64_t info[8]);
  *   d_eps       NULL, or [iters][B] float64: eps[i][b] = 1 - cos(x_{i+1}[:,b], stationary), clipped [0,2]
  *   d_ws        work space of at least cy2p_propagate_ws_bytes(plan, B, iters) bytes, 256-byte aligned
  * Arithmetic: fp32 products and row sums in ascending source order (the order scipy's csc_matvec
- * adds them, there in float64); eps dot products accumulate in float64. */
+ * adds them, there in float64); the eps dot products are summed per thread (4 rows) in the iterate's precision
+ * and across threads / CTAs in float64 (agreement with a float64 recomputation: ~1e-7 for fp32 iterates). */
 size_t cy2p_propagate_ws_bytes(const cy2p_plan *plan, int32_t B, int32_t iters);
 /* Width of the column tiles cy2p_propagate carries through all iterations (sized to stay L2-resident). */
 int32_t cy2p_propagate_column_tile(const cy2p_plan *plan, int32_t B);
