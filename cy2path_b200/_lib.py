@@ -258,7 +258,7 @@ def fhmm_forward(theta_pi, theta_w, theta_E, theta_A, num_iters, restricted, wan
 TERM_NAMES = ("loss", "divergence", "log_likelihood", "sparsity", "orthogonality", "exclusivity", "regularisation")
 
 
-def fhmm_loss_grad(plan, theta_pi, theta_w, theta_E, theta_A, D, restricted, weights, out=None):
+def fhmm_loss_grad(plan, theta_pi, theta_w, theta_E, theta_A, D, restricted, weights, out=None, terms=None):
     """cy2p_fhmm_loss_grad: one epoch's forward + loss + analytic gradients.
     weights = (sparsity, exclusivity, orthogonality, TPM). Returns (terms [8] cuda, (g_pi, g_w, g_E, g_A))."""
     torch = _torch()
@@ -276,10 +276,11 @@ def fhmm_loss_grad(plan, theta_pi, theta_w, theta_E, theta_A, D, restricted, wei
                    "g": tuple(torch.empty_like(t) for t in (tp, tw, tE, tA))}
         hw = (ctypes.c_float * 4)(*[float(x) for x in weights])
         g = out["g"]
+        tdst = out["terms"] if terms is None else terms  # 8 contiguous float32 (e.g. a row of the epoch history)
         check(lib.cy2p_fhmm_loss_grad(plan.handle, S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE),
-                                      ptr(tA), ptr(D), hw, ptr(out["terms"]), ptr(g[0]), ptr(g[1]), ptr(g[2]),
+                                      ptr(tA), ptr(D), hw, ptr(tdst), ptr(g[0]), ptr(g[1]), ptr(g[2]),
                                       ptr(g[3]), ptr(out["ws"]), out["nbytes"], stream_ptr(dev)))
-    return out["terms"], g, out
+    return tdst, g, out
 
 
 def fhmm_decode(theta_pi, theta_w, theta_E, theta_A, D, restricted):

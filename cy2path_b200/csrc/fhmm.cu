@@ -353,34 +353,69 @@ __global__ void fhmm_joint_kernel(int S, int L, int Le, int N, int I, const floa
 // The pass over D: pred, KL divergence, dDiv/dlogE (per t-split partials) and dDiv/dG.
 //   grid.x = column tiles (blockDim.x * J columns), grid.y = t splits of `tchunk` rows.
 //   Max-shifted per column: Ehat[k] = exp(logE[k,n] - m_n), Phat = sum_k G[t,k] Ehat[k], log P = m_n + log Phat.
+// Blackwell packed fp32 FMA (FFMA2): two independent fp32 FMAs per instruction on a register pair.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+// Sum NV values (power of two <= 32) across the 32 lanes with a transposing butterfly: every stage halves the
+// values a lane carries, so NV + log2(32/NV) shuffles replace 5*NV. Afterwards v[0] on lane `l` is the full sum of
+// element e(l) = (l >> log2(32/NV)) & (NV-1)  (every element is held by 32/NV lanes).
+template <int NV>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[NV], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int h = NV / 2; h >= 1; h /= 2, off /= 2) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = upper ? v[i] : v[i + h];
+            const float keep = upper ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    for (; off >= 1; off /= 2) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+__host__ __device__ constexpr int next_pow2(int x) { return x <= 1 ? 1 : x <= 2 ? 2 : x <= 4 ? 4 : x <= 8 ? 8 : x <= 16 ? 16 : x <= 32 ? 32 : 64; }
+__host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x / 2); }
+
+// Thread owns J columns (adjacent column PAIRS share FFMA2 instructions), loops over the rows of its t-split.
 template <int KP, int J>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (KP <= 12 ? 4 : 1))
 fhmm_data_pass(int N, int I, int K, int tchunk, const float *__restrict__ logE, const float *__restrict__ G,
                const float *__restrict__ D, float *__restrict__ pred, float *__restrict__ glogE_split,
                float *__restrict__ gG, double *__restrict__ div_acc, float inv_I) {
-    extern __shared__ float sG[];  // [tchunk][KP]
+    constexpr int JP = (J + 1) / 2;  // column pairs; J == 1 runs with a dead second half
+    extern __shared__ float sG[];    // [tchunk][KP]
     const int t0 = blockIdx.y * tchunk, t1 = min(I, t0 + tchunk);
     for (int i = threadIdx.x; i < (t1 - t0) * KP; i += blockDim.x) sG[i] = G[(size_t)t0 * KP + i];
     const int lane = threadIdx.x & 31;
     const int base = blockIdx.x * blockDim.x * J + threadIdx.x;
-    float Eh[J][KP], dE[J][KP], mcol[J];
-    bool ok[J];
+    float2 Eh[JP][KP], dE[JP][KP];
+    float mcol[2 * JP];
+    bool ok[2 * JP];
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
+    for (int j = 0; j < 2 * JP; ++j) {
         const int n = base + j * blockDim.x;
-        ok[j] = n < N;
+        ok[j] = j < J && n < N;
+        float e[KP];
         float m = -INFINITY;
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
-            Eh[j][k] = (ok[j] && k < K) ? logE[(size_t)k * N + n] : -INFINITY;
-            m = fmaxf(m, Eh[j][k]);
+            e[k] = (ok[j] && k < K) ? logE[(size_t)k * N + n] : -INFINITY;
+            m = fmaxf(m, e[k]);
         }
         if (!ok[j]) m = 0.f;
         mcol[j] = m;
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
-            Eh[j][k] = (ok[j] && k < K) ? expf(Eh[j][k] - m) : 0.f;
-            dE[j][k] = 0.f;
+            const float v = (ok[j] && k < K) ? expf(e[k] - m) : 0.f;
+            if (j & 1) Eh[j / 2][k].y = v;
+            else Eh[j / 2][k].x = v;
+            dE[j / 2][k] = make_float2(0.f, 0.f);
         }
     }
     __syncthreads();
@@ -388,47 +423,73 @@ fhmm_data_pass(int N, int I, int K, int tchunk, const float *__restrict__ logE, 
     for (int t = t0; t < t1; ++t) {
         float div_f = 0.f;  // per-row partial in float, promoted once per t
         const float *g = sG + (t - t0) * KP;
-        float part[KP];
+        float2 g2[KP];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) part[k] = 0.f;
+        for (int k = 0; k < KP; ++k) g2[k] = make_float2(g[k], g[k]);
+        float2 part2[KP];
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const int n = base + j * blockDim.x;
-            const float d = (ok[j] && D != nullptr) ? __ldg(D + (size_t)t * N + n) : 0.f;
-            float p = 0.f;
+        for (int k = 0; k < KP; ++k) part2[k] = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < KP; ++k) p = fmaf(g[k], Eh[j][k], p);
-            p = fmaxf(p, FLT_MIN);
-            if (pred != nullptr) {  // forward_model output: full-precision log
-                if (ok[j]) pred[(size_t)t * N + n] = mcol[j] + logf(p);
+        for (int jp = 0; jp < JP; ++jp) {
+            float2 p2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) p2 = ffma2(g2[k], Eh[jp][k], p2);
+            float pv[2] = {p2.x, p2.y}, rv[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * jp + h;
+                const int n = base + j * blockDim.x;
+                const float d = (ok[j] && D != nullptr) ? __ldg(D + (size_t)t * N + n) : 0.f;
+                const float p = fmaxf(pv[h], FLT_MIN);
+                if (pred != nullptr) {  // forward_model output: full-precision log
+                    if (ok[j]) pred[(size_t)t * N + n] = mcol[j] + logf(p);
+                }
+                float r = 0.f;
+                if (d > 0.f) {
+                    // loss pass: MUFU log2 / reciprocal (abs. error of the log ~5e-7, weighted by D whose rows sum to 1)
+                    r = __fdividef(d, p);
+                    div_f += d * (__logf(d) - mcol[j] - __logf(p));  // xlogy(D,D) - D*pred (KLDivLoss, trainer.py:139)
+                }
+                rv[h] = r;
             }
-            float r = 0.f;
-            if (d > 0.f) {
-                // loss pass: MUFU log2 / reciprocal (abs. error of the log ~5e-7, weighted by D whose rows sum to 1)
-                r = __fdividef(d, p);
-                div_f += d * (__logf(d) - mcol[j] - __logf(p));  // xlogy(D,D) - D*pred  (KLDivLoss, trainer.py:139)
-            }
+            const float2 r2 = make_float2(rv[0], rv[1]);
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
-                dE[j][k] = fmaf(r, g[k], dE[j][k]);
-                part[k] = fmaf(r, Eh[j][k], part[k]);
+                dE[jp][k] = ffma2(r2, g2[k], dE[jp][k]);
+                part2[k] = ffma2(r2, Eh[jp][k], part2[k]);
             }
         }
         div += (double)div_f;
+        // dG[t][k] = -(1/I) sum over the warp's columns: transposing butterfly, then one atomic per element
+        constexpr int NV = next_pow2(KP);
+        if (NV <= 32) {
+            float v[NV];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            const float s = warp_sum(part[k]);
-            if (lane == 0 && k < K && s != 0.f) atomicAdd(&gG[(size_t)t * K + k], -inv_I * s);
+            for (int k = 0; k < NV; ++k) v[k] = k < KP ? part2[k < KP ? k : 0].x + part2[k < KP ? k : 0].y : 0.f;
+            warp_transpose_reduce<NV>(v, lane);
+            constexpr int REP = 32 / NV;  // lanes holding the same element
+            const int e = (lane / REP) % NV;
+            if (lane % REP == 0 && e < K && v[0] != 0.f) atomicAdd(&gG[(size_t)t * K + e], -inv_I * v[0]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const float sacc = warp_sum(part2[k].x + part2[k].y);
+                if (lane == 0 && k < K && sacc != 0.f) atomicAdd(&gG[(size_t)t * K + k], -inv_I * sacc);
+            }
         }
     }
     float *out = glogE_split + (size_t)blockIdx.y * K * N;
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
+    for (int j = 0; j < 2 * JP; ++j) {
         const int n = base + j * blockDim.x;
         if (!ok[j]) continue;
 #pragma unroll
         for (int k = 0; k < KP; ++k)
-            if (k < K) out[(size_t)k * N + n] = -inv_I * Eh[j][k] * dE[j][k];
+            if (k < K) {
+                const float eh = (j & 1) ? Eh[j / 2][k].y : Eh[j / 2][k].x;
+                const float de = (j & 1) ? dE[j / 2][k].y : dE[j / 2][k].x;
+                out[(size_t)k * N + n] = -inv_I * eh * de;
+            }
     }
     div = warp_sum(div);
     __shared__ double sdiv[4];

@@ -83,9 +83,9 @@ def train(self, D, TPM=None, num_epochs=300, sparsity_weight=1.0, exclusivity_we
     bufs = None
     start_time = time.time()
     for epoch in range(num_epochs):
-        self.optimizer.zero_grad(set_to_none=False)
-        terms, grads, bufs = _lib.fhmm_loss_grad(plan, *[p.data for p in params], D, self.restricted, weights, out=bufs)
-        history[epoch].copy_(terms)
+        # cy2p_fhmm_loss_grad overwrites every gradient entry, so there is nothing to zero (trainer.py:130 zero_grad)
+        terms, grads, bufs = _lib.fhmm_loss_grad(plan, *[p.data for p in params], D, self.restricted, weights, out=bufs,
+                                                 terms=history[epoch])
         report = epoch % 100 == 99 or epoch <= 9
         if report:  # correlation of the (pre-step) prediction with the data, trainer.py:205-210
             pred = _lib.fhmm_forward(*[p.data for p in params], self.num_iters, self.restricted, want_pred=True)["pred"]
@@ -96,10 +96,10 @@ def train(self, D, TPM=None, num_epochs=300, sparsity_weight=1.0, exclusivity_we
             self.avg_corrcoeff = torch.mean(cc).item()
         for p, g in zip(params, grads):
             if p.requires_grad:
-                if p.grad is None:
-                    p.grad = g.clone()
-                else:
-                    p.grad.copy_(g)
+                if p.grad is not g:
+                    p.grad = g  # the kernel writes straight into the tensors the optimiser reads
+            else:
+                p.grad = None
         self.optimizer.step()
         if self.elapsed_epochs > swa_start and self.swa_scheduler is not None:
             swa_scheduler.step()
