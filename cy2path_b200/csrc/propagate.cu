@@ -85,20 +85,34 @@ struct Vec<double, 1> {
 // base pointers address. eps_acc (may be null): [kEpsCopies][ncols][2] doubles, (x.pi, x.x) partial sums of
 // this update; CTA b adds into copy b % kEpsCopies and eps_finalize_tile sums the copies.
 // The products are added in ascending source order — the order scipy's csc_matvec adds them.
+template <typename T>
+struct GatherArgs {
+    const int32_t *t_indptr;
+    const Pair *pairs;
+    const int32_t *dest_ids;
+    int32_t out_orig;
+    const T *Xin;
+    uint32_t ld_in;
+    T *Xout;
+    uint32_t ld_out;
+    int32_t ncols;
+    const double *stationary;
+    double *eps_acc;
+    T *const *peer_out;
+    int32_t npeers;
+};
+
+// Destination rows [row0, row1) x column slab `slab` (32*VEC columns) by one CTA; `copy_sel` picks the eps
+// accumulator copy this CTA adds to.
 template <typename T, int VEC, bool EPS>
-__global__ void __launch_bounds__(kWarps * 32, sizeof(T) == 4 ? 6 : 3)
-spmm_gather(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, const int32_t *__restrict__ t_indptr,
-            const Pair *__restrict__ pairs, const int32_t *__restrict__ dest_ids, int32_t out_orig,
-            const T *__restrict__ Xin, uint32_t ld_in, T *__restrict__ Xout, uint32_t ld_out, int32_t ncols,
-            const double *__restrict__ stationary, double *__restrict__ eps_acc, T *const *__restrict__ peer_out,
-            int32_t npeers) {
+__device__ __forceinline__ void gather_block(const GatherArgs<T> &a, int32_t row0, int32_t row1, int slab, int copy_sel) {
     using VT = Vec<T, VEC>;
     using V = typename VT::V;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = (blockIdx.y * 32 + lane) * VEC;
-    const bool active = col < ncols;
-    const int32_t row0 = row_begin + blockIdx.x * rows_per_cta;
-    const int32_t row1 = min(row0 + rows_per_cta, row_end);
+    const int col = (slab * 32 + lane) * VEC;
+    const bool active = col < a.ncols;
+    const uint32_t ld_in = a.ld_in, ld_out = a.ld_out;
+    const Pair *__restrict__ pairs = a.pairs;
     // cosine partial sums: a thread covers only rows_per_cta / kWarps rows, so its own partials are kept in the
     // iterate's precision (registers decide occupancy here, and the kernel is latency-bound); every sum across
     // warps and CTAs is float64
@@ -107,10 +121,10 @@ spmm_gather(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, const int3
     for (int k = 0; k < VEC; ++k) uv[k] = uu[k] = (T)0;
 
     if (active) {
-        const T *xin = Xin + col;
+        const T *__restrict__ xin = a.Xin + col;
         for (int32_t r = row0 + warp; r < row1; r += kWarps) {
-            int32_t p = t_indptr[r];
-            const int32_t end = t_indptr[r + 1];
+            int32_t p = __ldg(a.t_indptr + r);
+            const int32_t end = __ldg(a.t_indptr + r + 1);
             V acc = VT::zero();
             if (p < end && (p & 1)) {  // align the entry cursor to 16 bytes
                 const Pair e = pairs[p];
@@ -141,17 +155,17 @@ spmm_gather(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, const int3
                 const Pair e = pairs[p];
                 VT::fma(acc, e.val, VT::load(xin + (uint64_t)(uint32_t)e.src * ld_in));
             }
-            const int32_t cell = dest_ids ? __ldg(dest_ids + r) : r;
-            const uint64_t off = (uint64_t)(uint32_t)(out_orig ? cell : r) * ld_out + col;
-            if (peer_out == nullptr) {
-                VT::store(Xout + off, acc);
+            const int32_t cell = a.dest_ids ? __ldg(a.dest_ids + r) : r;
+            const uint64_t off = (uint64_t)(uint32_t)(a.out_orig ? cell : r) * ld_out + col;
+            if (a.peer_out == nullptr) {
+                VT::store(a.Xout + off, acc);
             } else {
                 // fused all-gather (row-partitioned propagation): the finished row goes straight into every rank's
                 // next-iterate buffer — local HBM for this rank, NVLink peer stores for the others
-                for (int32_t g = 0; g < npeers; ++g) VT::store(peer_out[g] + off, acc);
+                for (int32_t g = 0; g < a.npeers; ++g) VT::store(a.peer_out[g] + off, acc);
             }
             if (EPS) {
-                const T pi = (T)stationary[cell];
+                const T pi = (T)a.stationary[cell];
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
                     const T y = (T)VT::get(acc, k);
@@ -173,13 +187,53 @@ spmm_gather(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, const int3
         __syncthreads();
         for (int t = threadIdx.x; t < 2 * VEC * 32; t += kWarps * 32) {
             const int which = t / (VEC * 32), k = (t / 32) % VEC, ln = t & 31;
-            const int gcol = (blockIdx.y * 32 + ln) * VEC + k;
-            if (gcol < ncols) {
+            const int gcol = (slab * 32 + ln) * VEC + k;
+            if (gcol < a.ncols) {
                 double s = 0.0;
 #pragma unroll
                 for (int w = 0; w < kWarps; ++w) s += (double)red[which][k][w][ln];
-                atomicAdd(&eps_acc[((int64_t)(blockIdx.x % kEpsCopies) * ncols + gcol) * 2 + which], s);
+                atomicAdd(&a.eps_acc[((int64_t)copy_sel * a.ncols + gcol) * 2 + which], s);
             }
+        }
+        __syncthreads();  // `red` is reused by the next work item of a persistent CTA
+    }
+}
+
+// Grid version: blockIdx.x = row group, blockIdx.y = column slab.
+template <typename T, int VEC, bool EPS>
+__global__ void __launch_bounds__(kWarps * 32, sizeof(T) == 4 ? 6 : 3)
+spmm_gather(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, GatherArgs<T> a) {
+    const int32_t row0 = row_begin + blockIdx.x * rows_per_cta;
+    gather_block<T, VEC, EPS>(a, row0, min(row0 + rows_per_cta, row_end), blockIdx.y, blockIdx.x % kEpsCopies);
+}
+
+// Persistent, SM-affine version for the long batched runs: SM s owns the contiguous row groups
+// [s*R, (s+1)*R) for every column slab and its resident CTAs draw them from a per-SM counter, slab by slab, so the
+// ~6 CTAs of an SM work on ADJACENT row groups of the SAME slab at the same time. In the plan's locality order
+// adjacent rows share sources, which turns part of the L2->SM fill traffic into L1 hits. A CTA whose SM has run dry
+// steals from the other SMs' queues. counters: [num_sms] ints, zero at launch.
+template <typename T, int VEC, bool EPS>
+__global__ void __launch_bounds__(kWarps * 32, sizeof(T) == 4 ? 6 : 3)
+spmm_gather_sm(int32_t n_rows, int32_t rows_per_cta, int32_t nslabs, int32_t num_sms, int32_t *__restrict__ counters,
+               GatherArgs<T> a) {
+    __shared__ int32_t s_item;
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const int32_t nrg = (n_rows + rows_per_cta - 1) / rows_per_cta;  // row groups
+    const int32_t R = (nrg + num_sms - 1) / num_sms;                 // row groups per SM
+    for (int32_t v = 0; v < num_sms; ++v) {
+        const int32_t owner = (int32_t)((smid + v) % (uint32_t)num_sms);
+        const int32_t rg0 = owner * R, cnt = max(0, min(nrg, rg0 + R) - rg0);
+        const int32_t total = cnt * nslabs;
+        for (;;) {
+            if (threadIdx.x == 0) s_item = total > 0 ? atomicAdd(&counters[owner], 1) : total;
+            __syncthreads();
+            const int32_t q = s_item;
+            __syncthreads();
+            if (q >= total) break;
+            const int32_t slab = q / cnt, rg = rg0 + q % cnt;
+            const int32_t row0 = rg * rows_per_cta;
+            gather_block<T, VEC, EPS>(a, row0, min(row0 + rows_per_cta, n_rows), slab, rg % kEpsCopies);
         }
     }
 }
@@ -489,9 +543,11 @@ static int32_t choose_tile(const cy2p_plan *plan, int32_t B, size_t elem) {
 }
 
 struct WsLayout {
-    size_t eps_acc, vv, bufA, bufB, total;
+    size_t eps_acc, vv, bufA, bufB, counters, total;
     int32_t tile;
 };
+constexpr int kCounterSlots = 8192;  // per-launch SM work counters, zeroed in blocks of this many launches
+constexpr int kMaxSms = 256;
 
 static WsLayout ws_layout(const cy2p_plan *plan, int32_t B, int32_t iters, size_t elem) {
     WsLayout w;
@@ -505,6 +561,8 @@ static WsLayout ws_layout(const cy2p_plan *plan, int32_t B, int32_t iters, size_
     off = align_up(off + elem * (size_t)plan->n * (size_t)w.tile, 256);
     w.bufB = off;
     off = align_up(off + elem * (size_t)plan->n * (size_t)w.tile, 256);
+    w.counters = off;
+    off = align_up(off + sizeof(int32_t) * (size_t)kCounterSlots * kMaxSms, 256);
     w.total = off;
     return w;
 }
@@ -523,22 +581,40 @@ struct GatherOperand {
 template <typename T, int VEC>
 static void launch_gather(const GatherOperand &g, int32_t row_begin, int32_t row_end, const T *in, uint32_t ld_in,
                           T *out, uint32_t ld_out, int32_t ncols, const double *stationary, double *eps_acc,
-                          cudaStream_t st) {
+                          cudaStream_t st, int32_t *sm_counters = nullptr, int32_t num_sms = 0) {
     static const int rows_per_cta = [] {
         int r = env_int("CY2P_ROWS_PER_CTA", 32);
         return r < kWarps ? kWarps : r;
     }();
-    dim3 grid((unsigned)((row_end - row_begin + rows_per_cta - 1) / rows_per_cta),
-              (unsigned)((ncols + 32 * VEC - 1) / (32 * VEC)));
+    GatherArgs<T> a;
+    a.t_indptr = g.indptr;
+    a.pairs = g.pairs;
+    a.dest_ids = g.dest_ids;
+    a.out_orig = g.out_orig;
+    a.Xin = in;
+    a.ld_in = ld_in;
+    a.Xout = out;
+    a.ld_out = ld_out;
+    a.ncols = ncols;
+    a.stationary = stationary;
+    a.eps_acc = eps_acc;
+    a.peer_out = (T *const *)g.peer_out;
+    a.npeers = g.npeers;
+    const int nslabs = (ncols + 32 * VEC - 1) / (32 * VEC);
     count_launch();
+    if (sm_counters != nullptr && row_begin == 0) {  // persistent SM-affine schedule (counters zeroed by the caller)
+        const int ctas = num_sms * (sizeof(T) == 4 ? 6 : 3);
+        if (eps_acc)
+            spmm_gather_sm<T, VEC, true><<<ctas, kWarps * 32, 0, st>>>(row_end, rows_per_cta, nslabs, num_sms, sm_counters, a);
+        else
+            spmm_gather_sm<T, VEC, false><<<ctas, kWarps * 32, 0, st>>>(row_end, rows_per_cta, nslabs, num_sms, sm_counters, a);
+        return;
+    }
+    dim3 grid((unsigned)((row_end - row_begin + rows_per_cta - 1) / rows_per_cta), (unsigned)nslabs);
     if (eps_acc)
-        spmm_gather<T, VEC, true><<<grid, kWarps * 32, 0, st>>>(row_begin, row_end, rows_per_cta, g.indptr, g.pairs,
-                                                               g.dest_ids, g.out_orig, in, ld_in, out, ld_out, ncols,
-                                                               stationary, eps_acc, (T *const *)g.peer_out, g.npeers);
+        spmm_gather<T, VEC, true><<<grid, kWarps * 32, 0, st>>>(row_begin, row_end, rows_per_cta, a);
     else
-        spmm_gather<T, VEC, false><<<grid, kWarps * 32, 0, st>>>(row_begin, row_end, rows_per_cta, g.indptr, g.pairs,
-                                                                g.dest_ids, g.out_orig, in, ld_in, out, ld_out, ncols,
-                                                                nullptr, nullptr, (T *const *)g.peer_out, g.npeers);
+        spmm_gather<T, VEC, false><<<grid, kWarps * 32, 0, st>>>(row_begin, row_end, rows_per_cta, a);
 }
 
 template <typename T>
@@ -734,6 +810,14 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
     }
     const bool reord = plan->reorder_state == 1;
     const GatherOperand ident = {plan->d_t_indptr, plan->d_t_pairs, nullptr, 0};
+    // SM-affine persistent schedule (experiment, off by default): measured SLOWER than the plain grid on B200
+    // (1.01e11 vs 1.23e11 cell-it/s at 50k cells, 0.81e11 vs 1.21e11 at 250k, profiles/k1_sweep5_sm_affine_r01.jsonl):
+    // the plain grid's wave front covers one contiguous band of the locality-ordered rows, which is what keeps the
+    // gathers in L2; 148 SMs working 148 distant bands lose that. CY2P_SM_AFFINE=1 enables it.
+    static const int sm_affine_env = env_int("CY2P_SM_AFFINE", 0);
+    const bool sm_affine = sm_affine_env && reord && n >= 8192 && plan->num_sms <= kMaxSms;
+    int32_t *counters = (int32_t *)(ws + w.counters);
+    int64_t launch_no = 0;
     for (int32_t c0 = 0; c0 < B; c0 += w.tile) {
         const int32_t nc = (B - c0 < w.tile) ? B - c0 : w.tile;
         if (d_eps)
@@ -765,10 +849,18 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
                 g.dest_ids = plan->d_order;
                 g.out_orig = dst_perm ? 0 : 1;
             }
+            int32_t *cnt = nullptr;
+            if (sm_affine && src_perm) {  // permuted -> permuted / permuted -> original updates
+                const int64_t slot = launch_no % kCounterSlots;
+                if (slot == 0)
+                    CY2P_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * (size_t)kCounterSlots * kMaxSms, st));
+                cnt = counters + slot * kMaxSms;
+                ++launch_no;
+            }
             if (wide && (nc % VW == 0))
-                launch_gather<T, VW>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st);
+                launch_gather<T, VW>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms);
             else
-                launch_gather<T, 1>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st);
+                launch_gather<T, 1>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms);
             src = dst;
             ld_src = ld_dst;
             src_perm = dst_perm;
