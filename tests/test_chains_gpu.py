@@ -147,3 +147,32 @@ def test_cluster_convergence_branch():
     u = ad.uns["markov_chain_sampling"]
     assert u["cluster_proportions_max_iter"].shape == (40, 2)
     assert 2 <= u["sampling_params"]["convergence"] <= 40
+
+
+def test_chain_edge_cases_single_step_and_absorbing_state():
+    import scipy.sparse as sp
+
+    import cy2path_b200 as c2p
+
+    # state 2 is absorbing (self loop), state 3 has an empty row: walking into it overshoots on the next step
+    indptr = np.array([0, 2, 4, 5, 5], dtype=np.int32)
+    indices = np.array([1, 2, 2, 3, 2], dtype=np.int32)
+    data = np.array([0.5, 0.5, 0.5, 0.5, 1.0], dtype=np.float32)
+    T = sp.csr_matrix((data, indices, indptr), shape=(4, 4))
+    ad = Duck(T)
+    idx, cum = c2p.extract_nonzero_entries(ad)
+    ridx, rcum = ochains.extract_nonzero_entries(T)
+    assert np.array_equal(idx, ridx) and np.array_equal(cum, rcum)
+    # max_iter == 1: no steps at all
+    s, p = c2p.iterate_markov_chain(ad, max_iter=1, init_state=1, uniforms=np.empty(0))
+    assert s.tolist() == [1] and p.shape == (0,)
+    # absorbing walk
+    u = np.array([0.9, 0.3, 0.99, 0.0])
+    s, p = c2p.iterate_markov_chain(ad, max_iter=5, init_state=0, uniforms=u)
+    rs, rp = ochains.sample_chains(T, idx, cum, np.array([0]), u[None, :])
+    assert np.array_equal(s, rs[0]) and np.array_equal(p, rp[0]) and s.tolist() == [0, 2, 2, 2, 2]
+    # 0 -> 1 -> 3, then the empty row raises like the reference
+    with pytest.raises(IndexError):
+        c2p.iterate_markov_chain(ad, max_iter=4, init_state=0, uniforms=np.array([0.2, 0.8, 0.5]))
+    with pytest.raises(IndexError):
+        ochains.sample_chains(T, idx, cum, np.array([0]), np.array([[0.2, 0.8, 0.5]]))

@@ -286,3 +286,50 @@ def test_drop_in_wrapper_keys():
     assert set(u["sampling_params"]) == {"recalc_matrix", "self_transitions", "init_type", "max_iter", "convergence",
                                          "tol", "copy"}
     assert u["state_history_max_iter"].shape == (50, 600)
+
+
+def test_edge_cases_tiny_graphs_empty_rows_and_short_runs():
+    """Cells without out-edges or in-edges, a 1-cell graph, max_iter of 1 and 0 updates."""
+    import scipy.sparse as sp
+    import torch
+
+    import cy2path_b200 as c2p
+    from cy2path_b200 import _lib
+
+    # 6 cells: cell 2 has no out-edges (empty CSR row), cell 4 has no in-edges
+    rows = np.array([0, 0, 1, 1, 3, 3, 4, 5, 5])
+    cols = np.array([1, 2, 0, 3, 2, 5, 0, 3, 5])
+    vals = np.array([0.5, 0.5, 0.25, 0.75, 0.4, 0.6, 1.0, 0.3, 0.7], dtype=np.float32)
+    T = sp.csr_matrix((vals, (rows, cols)), shape=(6, 6))
+    T.indices = T.indices.astype(np.int32)
+    T.indptr = T.indptr.astype(np.int32)
+    init = np.array([0.5, 0.0, 0.0, 0.0, 0.5, 0.0])
+    stat = np.full(6, 1 / 6)
+    ad = Duck(T)
+    _, hist, conv = c2p.iterate_state_probability(ad, init=init, stationary=stat, max_iter=12)
+    _, ref, rconv, _ = omsm.iterate_state_probability(T, init, stat, max_iter=12)
+    assert conv == rconv and np.abs(hist - ref).max() <= 1e-14
+    # batched, every small B, fp32 and fp64
+    plan = _lib.Plan(T)
+    for B in (1, 2, 5, 8):
+        X0 = np.random.default_rng(B).random((6, B)).astype(np.float32)
+        X0 /= X0.sum(0)
+        refB = ofast.propagate_batch(T, X0, 7)
+        for dt in (torch.float32, torch.float64):
+            got = _lib.propagate(plan, torch.from_numpy(X0).to(dt).cuda(), 7)["final"].cpu().numpy()
+            assert np.abs(got - refB).max() <= (1e-6 if dt == torch.float32 else 1e-14)
+    # zero updates returns the start; max_iter == 1 keeps only the start row
+    x = torch.from_numpy(X0).cuda()
+    assert torch.equal(_lib.propagate(plan, x, 0)["final"], x)
+    _, h1, c1 = c2p.iterate_state_probability(ad, init=init, stationary=stat, max_iter=1)
+    assert h1.shape == (1, 6) and c1 == 1 and np.array_equal(h1[0], init)
+    # a single absorbing cell
+    T1 = sp.csr_matrix(np.ones((1, 1), dtype=np.float32))
+    _, h, c = c2p.iterate_state_probability(Duck(T1), init=np.ones(1), stationary=np.ones(1), max_iter=5)
+    assert np.array_equal(h, np.ones((5, 1)))
+    # float64 user matrix and int64 indices are accepted (cast to the device layout)
+    T64 = sp.csr_matrix(T, dtype=np.float64)
+    T64.indices = T64.indices.astype(np.int64)
+    T64.indptr = T64.indptr.astype(np.int64)
+    _, h64, _ = c2p.iterate_state_probability(Duck(T64), init=init, stationary=stat, max_iter=12)
+    assert np.abs(h64 - ref).max() <= 1e-14
