@@ -12,13 +12,13 @@ __version__ = "0.1.0"
 
 __all__ = [
     "iterate_state_probability", "sample_state_probability", "check_convergence_criteria", "propagate_batch",
-    "extract_nonzero_entries", "iterate_markov_chain", "sample_markov_chains", "FHMM",
+    "extract_nonzero_entries", "iterate_markov_chain", "sample_markov_chains", "FHMM", "LSSM",
 ]
 
 
 def __getattr__(name):  # lazy: torch.nn is only imported when the model is used
-    if name == "FHMM":
-        from .models import FHMM
+    if name in ("FHMM", "LSSM"):
+        from . import models
 
-        return FHMM
+        return getattr(models, name)
     raise AttributeError(name)

@@ -24,7 +24,8 @@ SYMBOLS = [
     "cy2p_propagate_rows_ordered", "cy2p_propagate_rows_ordered_f64", "cy2p_propagate_rows_allgather",
     "cy2p_propagate_rows_allgather_f64", "cy2p_enable_peer_access", "cy2p_cdf_build",
     "cy2p_sample_chains", "cy2p_chain_history", "cy2p_fhmm_ws_bytes", "cy2p_fhmm_small_floats",
-    "cy2p_fhmm_forward", "cy2p_fhmm_loss_grad", "cy2p_fhmm_decode",
+    "cy2p_fhmm_forward", "cy2p_fhmm_loss_grad", "cy2p_fhmm_decode", "cy2p_lssm_ws_bytes", "cy2p_lssm_small_floats",
+    "cy2p_lssm_forward", "cy2p_lssm_loss_grad", "cy2p_lssm_decode",
 ]
 
 _lib = None
@@ -81,11 +82,20 @@ def load():
                                             ctypes.POINTER(ctypes.c_float), _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]
     if hasattr(lib, "cy2p_fhmm_decode"):
         lib.cy2p_fhmm_decode.argtypes = [_i32] * 5 + [_vp] * 14 + [_sz, _vp]
+    if hasattr(lib, "cy2p_lssm_forward"):
+        lib.cy2p_lssm_ws_bytes.argtypes = lib.cy2p_fhmm_ws_bytes.argtypes
+        lib.cy2p_lssm_ws_bytes.restype = _sz
+        lib.cy2p_lssm_small_floats.argtypes = [_i32, _i32]
+        lib.cy2p_lssm_small_floats.restype = _i32
+        lib.cy2p_lssm_forward.argtypes = lib.cy2p_fhmm_forward.argtypes
+        lib.cy2p_lssm_loss_grad.argtypes = lib.cy2p_fhmm_loss_grad.argtypes
+        lib.cy2p_lssm_decode.argtypes = lib.cy2p_fhmm_decode.argtypes
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and name not in ("cy2p_last_error", "cy2p_propagate_ws_bytes", "cy2p_fhmm_ws_bytes",
                                            "cy2p_fhmm_small_floats", "cy2p_abi_version", "cy2p_launch_count",
-                                           "cy2p_propagate_f64_ws_bytes"):
+                                           "cy2p_propagate_f64_ws_bytes", "cy2p_lssm_ws_bytes",
+                                           "cy2p_lssm_small_floats"):
             fn.restype = _i32
     _lib = lib
     return lib
@@ -219,33 +229,49 @@ def propagate(plan, X0, iters, stationary=None, want_final=True, history_stride=
 
 
 # ------------------------------------------------------------------------------------------ K3 (FHMM)
-def _fhmm_ws(S, L, N, I, dev):
+def _model_dims(model, theta_pi, theta_w):
+    """(S, L) of the FHMM (theta_pi [S,L], theta_w [L]) or the LSSM (theta_pi [S], theta_w [S,L])."""
+    if model == "fhmm":
+        return int(theta_pi.shape[0]), int(theta_pi.shape[1])
+    if model == "lssm":
+        return int(theta_w.shape[0]), int(theta_w.shape[1])
+    raise ValueError("model must be 'fhmm' or 'lssm'")
+
+
+def _fhmm_ws(S, L, N, I, dev, model="fhmm"):
     torch = _torch()
-    nbytes = load().cy2p_fhmm_ws_bytes(S, L, N, I)
+    nbytes = getattr(load(), "cy2p_%s_ws_bytes" % model)(S, L, N, I)
     if nbytes == 0:
         raise ValueError("unsupported model size (supported: S <= 32, L <= 16, S*(1 if restricted else L) <= 64)")
     return torch.empty(nbytes, dtype=torch.uint8, device=dev), nbytes
 
 
-def fhmm_forward(theta_pi, theta_w, theta_E, theta_A, num_iters, restricted, want_pred=True, want_joint=False):
-    """cy2p_fhmm_forward on cuda float32 parameter tensors. Returns dict of cuda tensors:
-    pred [I,N] | None, hidden [I,S,L], joint [I,S,L,N] | None, log_E [S,Le,N], log_pi, log_w, log_A, log_A_mix."""
+def fhmm_forward(theta_pi, theta_w, theta_E, theta_A, num_iters, restricted, want_pred=True, want_joint=False,
+                 model="fhmm"):
+    """cy2p_fhmm_forward / cy2p_lssm_forward on cuda float32 parameter tensors. Returns dict of cuda tensors:
+    pred [I,N] | None, hidden [I,S,L] ([I,S] for the LSSM), joint [I,S,L,N] | None, log_E [S,Le,N], log_pi, log_w,
+    log_A, log_A_mix (the LSSM has one transition matrix: log_A_mix is log_A)."""
     torch = _torch()
     lib = load()
-    S, L = theta_pi.shape
+    S, L = _model_dims(model, theta_pi, theta_w)
     Le, N = theta_E.shape[1], theta_E.shape[2]
     I = int(num_iters)
     dev = theta_pi.device
     tp, tw, tE, tA = (t.detach().contiguous().float() for t in (theta_pi, theta_w, theta_E, theta_A))
     with torch.cuda.device(dev):
-        ws, nbytes = _fhmm_ws(S, L, N, I, dev)
+        ws, nbytes = _fhmm_ws(S, L, N, I, dev, model)
         pred = torch.empty((I, N), dtype=torch.float32, device=dev) if want_pred else None
-        hidden = torch.empty((I, S, L), dtype=torch.float32, device=dev)
+        hidden = torch.empty((I, S, L) if model == "fhmm" else (I, S), dtype=torch.float32, device=dev)
         joint = torch.empty((I, S, L, N), dtype=torch.float32, device=dev) if want_joint else None
         logE = torch.empty((S, Le, N), dtype=torch.float32, device=dev)
-        small = torch.empty(lib.cy2p_fhmm_small_floats(S, L), dtype=torch.float32, device=dev)
-        check(lib.cy2p_fhmm_forward(S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE), ptr(tA), ptr(pred),
-                                    ptr(hidden), ptr(joint), ptr(logE), ptr(small), ptr(ws), nbytes, stream_ptr(dev)))
+        small = torch.empty(getattr(lib, "cy2p_%s_small_floats" % model)(S, L), dtype=torch.float32, device=dev)
+        fwd = getattr(lib, "cy2p_%s_forward" % model)
+        check(fwd(S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE), ptr(tA), ptr(pred),
+                  ptr(hidden), ptr(joint), ptr(logE), ptr(small), ptr(ws), nbytes, stream_ptr(dev)))
+    if model == "lssm":
+        log_pi, log_w, log_A = small[:S], small[S:S + S * L].view(S, L), small[S + S * L:].view(S, S)
+        return {"pred": pred, "hidden": hidden, "joint": joint, "log_E": logE, "log_pi": log_pi, "log_w": log_w,
+                "log_A": log_A, "log_A_mix": log_A}
     o = 0
     log_pi = small[o:o + S * L].view(S, L); o += S * L
     log_w = small[o:o + L]; o += L
@@ -258,12 +284,13 @@ def fhmm_forward(theta_pi, theta_w, theta_E, theta_A, num_iters, restricted, wan
 TERM_NAMES = ("loss", "divergence", "log_likelihood", "sparsity", "orthogonality", "exclusivity", "regularisation")
 
 
-def fhmm_loss_grad(plan, theta_pi, theta_w, theta_E, theta_A, D, restricted, weights, out=None, terms=None):
-    """cy2p_fhmm_loss_grad: one epoch's forward + loss + analytic gradients.
+def fhmm_loss_grad(plan, theta_pi, theta_w, theta_E, theta_A, D, restricted, weights, out=None, terms=None,
+                   model="fhmm"):
+    """cy2p_fhmm_loss_grad / cy2p_lssm_loss_grad: one epoch's forward + loss + analytic gradients.
     weights = (sparsity, exclusivity, orthogonality, TPM). Returns (terms [8] cuda, (g_pi, g_w, g_E, g_A))."""
     torch = _torch()
     lib = load()
-    S, L = theta_pi.shape
+    S, L = _model_dims(model, theta_pi, theta_w)
     N = theta_E.shape[2]
     I = int(D.shape[0])
     dev = theta_pi.device
@@ -271,35 +298,38 @@ def fhmm_loss_grad(plan, theta_pi, theta_w, theta_E, theta_A, D, restricted, wei
     assert D.is_cuda and D.dtype == torch.float32 and D.is_contiguous() and D.shape[1] == N
     with torch.cuda.device(dev):
         if out is None:
-            ws, nbytes = _fhmm_ws(S, L, N, I, dev)
+            ws, nbytes = _fhmm_ws(S, L, N, I, dev, model)
             out = {"ws": ws, "nbytes": nbytes, "terms": torch.empty(8, dtype=torch.float32, device=dev),
                    "g": tuple(torch.empty_like(t) for t in (tp, tw, tE, tA))}
         hw = (ctypes.c_float * 4)(*[float(x) for x in weights])
         g = out["g"]
         tdst = out["terms"] if terms is None else terms  # 8 contiguous float32 (e.g. a row of the epoch history)
-        check(lib.cy2p_fhmm_loss_grad(plan.handle, S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE),
-                                      ptr(tA), ptr(D), hw, ptr(tdst), ptr(g[0]), ptr(g[1]), ptr(g[2]),
-                                      ptr(g[3]), ptr(out["ws"]), out["nbytes"], stream_ptr(dev)))
+        fn = getattr(lib, "cy2p_%s_loss_grad" % model)
+        check(fn(plan.handle, S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE), ptr(tA), ptr(D), hw,
+                 ptr(tdst), ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), ptr(out["ws"]), out["nbytes"],
+                 stream_ptr(dev)))
     return tdst, g, out
 
 
-def fhmm_decode(theta_pi, theta_w, theta_E, theta_A, D, restricted):
-    """cy2p_fhmm_decode: filtering, smoothing and viterbi in one call. Returns a dict of cuda tensors."""
+def fhmm_decode(theta_pi, theta_w, theta_E, theta_A, D, restricted, model="fhmm"):
+    """cy2p_fhmm_decode / cy2p_lssm_decode: filtering, smoothing and viterbi in one call. Returns a dict of cuda
+    tensors."""
     torch = _torch()
     lib = load()
-    S, L = theta_pi.shape
+    S, L = _model_dims(model, theta_pi, theta_w)
     N = theta_E.shape[2]
     I = int(D.shape[0])
     dev = theta_pi.device
     tp, tw, tE, tA = (t.detach().contiguous().float() for t in (theta_pi, theta_w, theta_E, theta_A))
     D = D.to(dev, dtype=torch.float32).contiguous()
     with torch.cuda.device(dev):
-        ws, nbytes = _fhmm_ws(S, L, N, I, dev)
+        ws, nbytes = _fhmm_ws(S, L, N, I, dev, model)
         f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)  # noqa: E731
         out = {"log_alpha": f(I, S, L), "log_probs": f(I, L), "log_beta": f(I, S, L), "log_gamma": f(I, S, L),
                "log_delta": f(I, S, L), "psi": f(I, S, L), "log_max": f(I, L), "best_path": f(L, I)}
-        check(lib.cy2p_fhmm_decode(S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE), ptr(tA), ptr(D),
-                                   ptr(out["log_alpha"]), ptr(out["log_probs"]), ptr(out["log_beta"]),
-                                   ptr(out["log_gamma"]), ptr(out["log_delta"]), ptr(out["psi"]), ptr(out["log_max"]),
-                                   ptr(out["best_path"]), ptr(ws), nbytes, stream_ptr(dev)))
+        fn = getattr(lib, "cy2p_%s_decode" % model)
+        check(fn(S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE), ptr(tA), ptr(D),
+                 ptr(out["log_alpha"]), ptr(out["log_probs"]), ptr(out["log_beta"]), ptr(out["log_gamma"]),
+                 ptr(out["log_delta"]), ptr(out["psi"]), ptr(out["log_max"]), ptr(out["best_path"]), ptr(ws), nbytes,
+                 stream_ptr(dev)))
     return out

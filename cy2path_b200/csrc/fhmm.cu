@@ -812,6 +812,31 @@ __global__ void __launch_bounds__(256) lse_combine(int nparts, const double2 *__
     }
 }
 
+// the 8 reported scalars (trainer.py:139-196): loss, divergence, log_likelihood, sparsity, orthogonality, exclusivity,
+// regularisation, reserved
+__device__ void write_terms(int S, int L, int K, const double *__restrict__ scal, float sparsity, float w_sparse,
+                            float w_excl, float w_orth, float w_tpm, float *__restrict__ terms) {
+    const ScalarOffsets sc(S, L, K);
+    const float divergence = (float)scal[sc.div];
+    float orth = 0.f;
+    for (int s0 = 0; s0 < S; ++s0) orth += (float)scal[sc.KL + s0];
+    orth /= (float)S;
+    float excl = 0.f;
+    if (L > 1) {
+        for (int l = 0; l < L; ++l) excl -= logf((float)scal[sc.d + l]);
+        excl /= (float)L;
+    }
+    const float reg = (float)(scal[sc.reg] / (double)S);
+    terms[0] = divergence + w_sparse * sparsity + w_orth * orth + (L > 1 ? w_excl * excl : 0.f) + w_tpm * reg;
+    terms[1] = divergence;
+    terms[2] = (float)scal[sc.ll];
+    terms[3] = sparsity;
+    terms[4] = orth;
+    terms[5] = excl;
+    terms[6] = reg;
+    terms[7] = 0.f;
+}
+
 // --------------------------------------------------------------------------------------------------
 // Backward of the hidden recurrence. With c_t[s,l] = w_l gG_t[s,l] + glogC[s,l] / (I Hbar[s,l]) the adjoint is
 //     gH_t = c_t + A_l gH_{t+1}          (gH_I = 0),
@@ -1023,26 +1048,7 @@ fhmm_small_backward(int S, int L, int I, int P, int restricted, int K, const flo
             sum += g;
         }
         for (int l = 0; l < L; ++l) g_w[l] = glw[l] - s_w[l] * sum;
-        // scalar terms
-        const float divergence = (float)scal[sc.div];
-        const float sparsity = aux[ao.sparsity];
-        float orth = 0.f;
-        for (int s0 = 0; s0 < S; ++s0) orth += (float)scal[sc.KL + s0];
-        orth /= (float)S;
-        float excl = 0.f;
-        if (L > 1) {
-            for (int l = 0; l < L; ++l) excl -= logf((float)scal[sc.d + l]);
-            excl /= (float)L;
-        }
-        const float reg = (float)(scal[sc.reg] / (double)S);
-        terms[0] = divergence + w_sparse * sparsity + w_orth * orth + (L > 1 ? w_excl * excl : 0.f) + w_tpm * reg;
-        terms[1] = divergence;
-        terms[2] = (float)scal[sc.ll];
-        terms[3] = sparsity;
-        terms[4] = orth;
-        terms[5] = excl;
-        terms[6] = reg;
-        terms[7] = 0.f;
+        write_terms(S, L, K, scal, aux[ao.sparsity], w_sparse, w_excl, w_orth, w_tpm, terms);
     }
 }
 
@@ -1223,6 +1229,172 @@ fhmm_decode_small(int S, int L, int Le, int I, const float *__restrict__ small, 
     }
 }
 
+// --------------------------------------------------------------------------------------------------
+// LSSM (reference models/_LSSM.py:7-117): ONE latent chain with state-level lineage weights,
+//     joint[t,s,l,n] = logE[s,e(l),n] + log w[s,l] + hidden[t,s],      hidden_t = hidden_{t-1} . A.
+// The chain is the FHMM recurrence with a single lineage, so the blocked forward / backward kernels above run with
+// L = 1; the kernels below mix the lineage weights in and out:
+//   forward : G[t,(s,l)] = w[s,l] H_t[s] (G[t,s] = H_t[s] when the emission is shared), C[s,l] = w[s,l] Hbar[s]
+//   backward: gG1[t,s] = sum_l w[s,l] gG[t,(s,l)], glogC1[s] = sum_l glogC[s,l], and the softmax Jacobian of theta_w
+//   small layout: log_pi[S] | log_w[S*L] | log_A[S*S]
+struct LssmSmallOffsets {
+    int log_pi, log_w, log_A, total;
+    __host__ __device__ LssmSmallOffsets(int S, int L) {
+        log_pi = 0;
+        log_w = S;
+        log_A = log_w + S * L;
+        total = log_A + S * S;
+    }
+};
+
+__global__ void __launch_bounds__(512)
+lssm_mix_forward(int S, int L, int I, int restricted, int KP, const float *__restrict__ theta_w,
+                 const float *__restrict__ small1, const float *__restrict__ aux1, const double *__restrict__ Hlin1,
+                 float *__restrict__ lsmall, float *__restrict__ G, float *__restrict__ aux) {
+    const SmallOffsets so1(S, 1);
+    const AuxOffsets ao1(S, 1), ao(S, L);
+    const LssmSmallOffsets lo(S, L);
+    __shared__ float s_logw[kMaxS * kMaxL], s_logC[kMaxS * kMaxL];
+    const int tid = threadIdx.x, nt = blockDim.x, SL = S * L;
+    for (int s = tid; s < S; s += nt) {  // log_softmax(theta_w, dim=-1)  (methods.py:12-14)
+        const float *x = theta_w + s * L;
+        float m = -INFINITY;
+        for (int l = 0; l < L; ++l) m = fmaxf(m, x[l]);
+        float z = 0.f;
+        for (int l = 0; l < L; ++l) z += expf(x[l] - m);
+        const float lse = m + logf(z);
+        for (int l = 0; l < L; ++l) {
+            s_logw[s * L + l] = x[l] - lse;
+            lsmall[lo.log_w + s * L + l] = x[l] - lse;
+        }
+        lsmall[lo.log_pi + s] = small1[so1.log_pi + s];
+    }
+    for (int i = tid; i < S * S; i += nt) lsmall[lo.log_A + i] = small1[so1.log_A + i];
+    __syncthreads();
+    for (int e = tid; e < SL; e += nt) {
+        const float lc = s_logw[e] + aux1[ao1.logC + e / L];  // log w[s,l] + log Hbar[s]
+        s_logC[e] = lc;
+        aux[ao.logC + e] = lc;
+        aux[ao.Hbar + e] = aux1[ao1.Hbar + e / L];
+    }
+    if (tid == 0) aux[ao.sparsity] = aux1[ao1.sparsity];
+    if (restricted) {
+        for (int i = tid; i < I * KP; i += nt) {
+            const int t = i / KP, k = i % KP;
+            G[i] = k < S ? (float)Hlin1[(size_t)t * S + k] : 0.f;  // sum_l w[s,l] = 1
+        }
+    } else {
+        for (int i = tid; i < I * KP; i += nt) {
+            const int t = i / KP, k = i % KP;
+            G[i] = k < SL ? (float)Hlin1[(size_t)t * S + k / L] * expf(s_logw[k]) : 0.f;
+        }
+    }
+    __syncthreads();
+    for (int s0 = tid; s0 < S; s0 += nt) {
+        float m = -INFINITY;
+        for (int ll = 0; ll < L; ++ll) m = fmaxf(m, s_logC[s0 * L + ll]);
+        float z = 0.f;
+        for (int ll = 0; ll < L; ++ll) z += expf(s_logC[s0 * L + ll] - m);
+        aux[ao.logc + s0] = m + logf(z);
+    }
+    for (int ll = tid; ll < L; ll += nt) {
+        float m = -INFINITY;
+        for (int s0 = 0; s0 < S; ++s0) m = fmaxf(m, s_logC[s0 * L + ll]);
+        float z = 0.f;
+        for (int s0 = 0; s0 < S; ++s0) z += expf(s_logC[s0 * L + ll] - m);
+        aux[ao.logq + ll] = m + logf(z);
+    }
+}
+
+// joint[t,s,l,n] = logE[s,e(l),n] + log w[s,l] + hidden[t,s]   (_LSSM.py:98-111)
+__global__ void lssm_joint_kernel(int S, int L, int Le, int N, int I, const float *__restrict__ logE,
+                                  const float *__restrict__ hidden, const float *__restrict__ log_w,
+                                  float *__restrict__ joint) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tsl = blockIdx.y;  // t*S*L + s*L + l
+    if (n >= N) return;
+    const int l = tsl % L, s = (tsl / L) % S, t = tsl / (S * L);
+    const int e = Le == 1 ? 0 : l;
+    joint[(size_t)tsl * N + n] = logE[(size_t)(s * Le + e) * N + n] + log_w[s * L + l] + hidden[t * S + s];
+}
+
+// grid = S CTAs (one latent state each). Folds the lineage axis of dLoss/dG and dLoss/dlogC onto the single chain
+// and finishes the theta_w gradient; CTA 0 writes the 8 scalars.
+__global__ void __launch_bounds__(256)
+lssm_glue_backward(int S, int L, int I, int restricted, int K, const float *__restrict__ lsmall,
+                   const double *__restrict__ Hlin1, const float *__restrict__ gG, const double *__restrict__ scal,
+                   const float *__restrict__ aux, float w_sparse, float w_excl, float w_orth, float w_tpm,
+                   float *__restrict__ gG1, double *__restrict__ scal1, float *__restrict__ g_w,
+                   float *__restrict__ terms) {
+    const LssmSmallOffsets lo(S, L);
+    const ScalarOffsets sc(S, L, K), sc1(S, 1, S);
+    const AuxOffsets ao(S, L);
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ float s_w[kMaxL], s_red[8][kMaxL];
+    if (tid < L) s_w[tid] = expf(lsmall[lo.log_w + s * L + tid]);
+    __syncthreads();
+    float acc[kMaxL];
+#pragma unroll
+    for (int l = 0; l < kMaxL; ++l) acc[l] = 0.f;
+    for (int t = tid; t < I; t += blockDim.x) {
+        const float h = (float)Hlin1[(size_t)t * S + s];
+        if (restricted) {
+            gG1[(size_t)t * S + s] = gG[(size_t)t * K + s];  // d/dw vanishes: sum_l w[s,l] is constant
+        } else {
+            float sum = 0.f;
+#pragma unroll
+            for (int l = 0; l < kMaxL; ++l)
+                if (l < L) {
+                    const float g = gG[(size_t)t * K + s * L + l];
+                    sum = fmaf(s_w[l], g, sum);
+                    acc[l] = fmaf(g, h, acc[l]);
+                }
+            gG1[(size_t)t * S + s] = sum;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < kMaxL; ++l)
+        if (l < L) {
+            const float v = warp_sum(acc[l]);
+            if (lane == 0) s_red[warp][l] = v;
+        }
+    __syncthreads();
+    if (tid == 0) {
+        const int nw = blockDim.x >> 5;
+        float glw[kMaxL], tot = 0.f;
+        double gc = 0.0;
+        for (int l = 0; l < L; ++l) {
+            float gp = 0.f;
+            for (int w = 0; w < nw; ++w) gp += s_red[w][l];
+            const double glc = scal[sc.glogC + s * L + l];
+            glw[l] = s_w[l] * gp + (float)glc;
+            tot += glw[l];
+            gc += glc;
+        }
+        for (int l = 0; l < L; ++l) g_w[s * L + l] = glw[l] - s_w[l] * tot;
+        scal1[sc1.glogC + s] = gc;
+        if (s == 0) write_terms(S, L, K, scal, aux[ao.sparsity], w_sparse, w_excl, w_orth, w_tpm, terms);
+    }
+}
+
+// Decoder inputs of the LSSM (_LSSM.py:120-260) in the FHMM decoder's layout: every lineage sees the same pi and A,
+// and the state-level weight joins the emission term: Bexp[t,(s,l)] = Bmat[t,k(s,l)] + log w[s,l].
+__global__ void lssm_expand_decode(int S, int L, int Le, int I, const float *__restrict__ lsmall,
+                                   const float *__restrict__ Bmat, float *__restrict__ small_exp,
+                                   float *__restrict__ Bexp) {
+    const LssmSmallOffsets lo(S, L);
+    const SmallOffsets so(S, L);
+    const int SL = S * L, K = S * Le;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
+    for (int i = gid; i < SL; i += gn) small_exp[so.log_pi + i] = lsmall[lo.log_pi + i / L];
+    for (int i = gid; i < L; i += gn) small_exp[so.log_w + i] = 0.f;
+    for (int i = gid; i < L * S * S; i += gn) small_exp[so.log_A + i] = lsmall[lo.log_A + i % (S * S)];
+    for (int i = gid; i < I * SL; i += gn) {
+        const int t = i / SL, e = i % SL, s = e / L, l = e % L;
+        Bexp[i] = Bmat[(size_t)t * K + s * Le + (Le == 1 ? 0 : l)] + lsmall[lo.log_w + e];
+    }
+}
+
 }  // namespace cy2p
 
 using namespace cy2p;
@@ -1343,9 +1515,7 @@ int32_t check_dims(int S, int L, int N, int I, int restricted) {
 }
 
 // forward pieces shared by cy2p_fhmm_forward and cy2p_fhmm_loss_grad
-int32_t run_forward(int S, int L, int Le, int N, int I, int restricted, const float *theta_pi, const float *theta_w,
-                    const float *theta_E, const float *theta_A, const FhmmWs &w, char *ws, cudaStream_t st) {
-    const int K = S * Le;
+int32_t run_emission(int K, int N, const float *theta_E, const FhmmWs &w, char *ws, cudaStream_t st) {
     float *logE = (float *)(ws + w.logE);
     const int nchunks = (N + kSoftmaxChunk - 1) / kSoftmaxChunk;
     CY2P_CUDA(cudaMemsetAsync(ws + w.row_lse, 0, sizeof(double) * K, st));
@@ -1354,6 +1524,13 @@ int32_t run_forward(int S, int L, int Le, int N, int I, int restricted, const fl
     count_launch();
     emission_softmax_write<<<dim3(K, nchunks), 256, 0, st>>>(N, theta_E, (const float2 *)(ws + w.partials), logE,
                                                               (double *)(ws + w.row_lse));
+    return CY2P_OK;
+}
+
+int32_t run_forward(int S, int L, int Le, int N, int I, int restricted, const float *theta_pi, const float *theta_w,
+                    const float *theta_E, const float *theta_A, const FhmmWs &w, char *ws, cudaStream_t st) {
+    int32_t rc = run_emission(S * Le, N, theta_E, w, ws, st);
+    if (rc) return rc;
     if (w.smem_fwd > 220 * 1024 || w.smem_bwd > 220 * 1024) {
         set_error("model too large for the one-CTA recurrence kernels (S=%d, L=%d, I=%d)", S, L, I);
         return CY2P_ERR_INVALID_ARG;
@@ -1364,6 +1541,70 @@ int32_t run_forward(int S, int L, int Le, int N, int I, int restricted, const fl
                                                    (float *)(ws + w.small), (float *)(ws + w.hidden),
                                                    (float *)(ws + w.G), (float *)(ws + w.aux), (double *)(ws + w.Hlin),
                                                    (double *)(ws + w.Apow));
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+// ---- LSSM: the FHMM work space (for the node / data passes with L lineages) plus the single-chain pieces
+struct LssmWs {
+    FhmmWs f;
+    size_t small1, aux1, scal1, gG1, G1, Apow1, lsmall, zero, tmp, total;
+    int P1, KP1;
+    size_t smem_fwd1, smem_bwd1, smem_local1;
+};
+
+LssmWs lssm_layout(int S, int L, int Le, int N, int I) {
+    LssmWs w;
+    w.f = fhmm_layout(S, L, Le, N, I);
+    w.P1 = choose_block(S, 1, I, &w.smem_fwd1, &w.smem_bwd1);
+    w.smem_local1 = sizeof(float) * (size_t)S * (S | 1);
+    w.KP1 = round_kp(S);
+    size_t off = w.f.total;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = up(off + bytes);
+        return o;
+    };
+    w.small1 = take(sizeof(float) * SmallOffsets(S, 1).total);
+    w.aux1 = take(sizeof(float) * AuxOffsets(S, 1).total);
+    w.scal1 = take(sizeof(double) * ScalarOffsets(S, 1, S).total);
+    w.gG1 = take(sizeof(float) * (size_t)I * S);
+    w.G1 = take(sizeof(float) * (size_t)I * w.KP1);
+    w.Apow1 = take(sizeof(double) * (size_t)w.P1 * S * S);
+    w.lsmall = take(sizeof(float) * LssmSmallOffsets(S, L).total);
+    w.zero = take(sizeof(float) * 4);
+    w.tmp = take(sizeof(float) * 16);  // discarded outputs of the single-lineage backward (g_w, terms)
+    w.total = off;
+    return w;
+}
+
+int32_t lssm_check_ws(const LssmWs &w, const void *d_ws, size_t ws_bytes) {
+    if (!d_ws || ws_bytes < w.total || ((uintptr_t)d_ws & 255)) {
+        set_error("work space too small or misaligned: need %zu bytes, 256-byte aligned", w.total);
+        return CY2P_ERR_WORKSPACE;
+    }
+    return CY2P_OK;
+}
+
+int32_t lssm_run_forward(int S, int L, int Le, int N, int I, int restricted, const float *theta_pi, const float *theta_w,
+                         const float *theta_E, const float *theta_A, const LssmWs &w, char *ws, cudaStream_t st) {
+    int32_t rc = run_emission(S * Le, N, theta_E, w.f, ws, st);
+    if (rc) return rc;
+    if (w.smem_fwd1 > 220 * 1024 || w.smem_bwd1 > 220 * 1024) {
+        set_error("model too large for the one-CTA recurrence kernels (S=%d, I=%d)", S, I);
+        return CY2P_ERR_INVALID_ARG;
+    }
+    CY2P_CUDA(cudaMemsetAsync(ws + w.zero, 0, sizeof(float) * 4, st));  // theta_w of the single lineage
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_fwd1));
+    count_launch();
+    fhmm_small_forward<<<1, 512, w.smem_fwd1, st>>>(S, 1, I, 1, w.KP1, w.P1, theta_pi, (const float *)(ws + w.zero),
+                                                    theta_A, (float *)(ws + w.small1), (float *)(ws + w.f.hidden),
+                                                    (float *)(ws + w.G1), (float *)(ws + w.aux1),
+                                                    (double *)(ws + w.f.Hlin), (double *)(ws + w.Apow1));
+    count_launch();
+    lssm_mix_forward<<<1, 512, 0, st>>>(S, L, I, restricted, w.f.KP, theta_w, (const float *)(ws + w.small1),
+                                        (const float *)(ws + w.aux1), (const double *)(ws + w.f.Hlin),
+                                        (float *)(ws + w.lsmall), (float *)(ws + w.f.G), (float *)(ws + w.f.aux));
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }
@@ -1536,6 +1777,170 @@ int32_t cy2p_fhmm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t res
     count_launch();
     fhmm_decode_small<<<1, 512, smem, st>>>(S, L, Le, I, (const float *)(ws + w.small), bm, d_log_alpha, d_log_probs,
                                             d_log_beta, d_log_gamma, d_log_delta, d_psi, d_log_max, d_best_path);
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ LSSM
+size_t cy2p_lssm_ws_bytes(int32_t S, int32_t L, int32_t N, int32_t I) {
+    if (S < 1 || L < 1 || N < 1 || I < 1 || S > kMaxS || L > kMaxL) return 0;
+    const LssmWs a = lssm_layout(S, L, 1, N, I);
+    if (S * L > kMaxK) return a.total;
+    const LssmWs b = lssm_layout(S, L, L, N, I);
+    return a.total > b.total ? a.total : b.total;
+}
+
+int32_t cy2p_lssm_small_floats(int32_t S, int32_t L) { return LssmSmallOffsets(S, L).total; }
+
+int32_t cy2p_lssm_forward(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted, const float *theta_pi,
+                          const float *theta_w, const float *theta_E, const float *theta_A, float *d_pred,
+                          float *d_hidden, float *d_joint, float *d_logE, float *d_small, void *d_ws, size_t ws_bytes,
+                          void *stream) {
+    int32_t rc = check_dims(S, L, N, I, restricted);
+    if (rc) return rc;
+    CY2P_REQUIRE(theta_pi && theta_w && theta_E && theta_A, "null parameter");
+    const int Le = restricted ? 1 : L, K = S * Le;
+    const LssmWs w = lssm_layout(S, L, Le, N, I);
+    if ((rc = lssm_check_ws(w, d_ws, ws_bytes))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    rc = lssm_run_forward(S, L, Le, N, I, restricted, theta_pi, theta_w, theta_E, theta_A, w, ws, st);
+    if (rc) return rc;
+    const float *logE = (const float *)(ws + w.f.logE);
+    if (d_pred) {
+        CY2P_CUDA(cudaMemsetAsync(ws + w.f.gG, 0, sizeof(float) * (size_t)I * K, st));
+        CY2P_CUDA(cudaMemsetAsync(ws + w.f.scal, 0, sizeof(double) * ScalarOffsets(S, L, K).total, st));
+        dispatch_data_pass(N, I, K, w.f, logE, (const float *)(ws + w.f.G), nullptr, d_pred, (float *)(ws + w.f.split),
+                           (float *)(ws + w.f.gG), (double *)(ws + w.f.scal), st);
+    }
+    if (d_hidden)
+        CY2P_CUDA(cudaMemcpyAsync(d_hidden, ws + w.f.hidden, sizeof(float) * (size_t)I * S, cudaMemcpyDeviceToDevice, st));
+    if (d_logE)
+        CY2P_CUDA(cudaMemcpyAsync(d_logE, logE, sizeof(float) * (size_t)K * N, cudaMemcpyDeviceToDevice, st));
+    if (d_small)
+        CY2P_CUDA(cudaMemcpyAsync(d_small, ws + w.lsmall, sizeof(float) * LssmSmallOffsets(S, L).total,
+                                  cudaMemcpyDeviceToDevice, st));
+    if (d_joint) {
+        dim3 grid((unsigned)((N + 255) / 256), (unsigned)(I * S * L));
+        count_launch();
+        lssm_joint_kernel<<<grid, 256, 0, st>>>(S, L, Le, N, I, logE, (const float *)(ws + w.f.hidden),
+                                                (const float *)(ws + w.lsmall) + LssmSmallOffsets(S, L).log_w, d_joint);
+    }
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+int32_t cy2p_lssm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted,
+                            const float *theta_pi, const float *theta_w, const float *theta_E, const float *theta_A,
+                            const float *d_D, const float *h_weights, float *d_terms, float *d_gpi, float *d_gw,
+                            float *d_gE, float *d_gA, void *d_ws, size_t ws_bytes, void *stream) {
+    int32_t rc = check_dims(S, L, N, I, restricted);
+    if (rc) return rc;
+    CY2P_REQUIRE(plan && theta_pi && theta_w && theta_E && theta_A && d_D && h_weights, "null pointer");
+    CY2P_REQUIRE(d_terms && d_gpi && d_gw && d_gE && d_gA, "null output");
+    CY2P_REQUIRE(plan->n == N, "plan size != num_nodes");
+    const int Le = restricted ? 1 : L, K = S * Le;
+    const LssmWs w = lssm_layout(S, L, Le, N, I);
+    if ((rc = lssm_check_ws(w, d_ws, ws_bytes))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CY2P_CUDA(cudaSetDevice(plan->device));
+    char *ws = (char *)d_ws;
+    const float w_sparse = h_weights[0], w_excl = h_weights[1], w_orth = h_weights[2], w_tpm = h_weights[3];
+    const ScalarOffsets sc(S, L, K);
+    float *logE = (float *)(ws + w.f.logE);
+    double *scal = (double *)(ws + w.f.scal), *scal1 = (double *)(ws + w.scal1);
+    const float *aux = (const float *)(ws + w.f.aux);
+    float *X1 = (float *)(ws + w.f.X1), *X2 = (float *)(ws + w.f.X2), *Y1 = (float *)(ws + w.f.Y1),
+          *TP = (float *)(ws + w.f.TP);
+
+    CY2P_CUDA(cudaMemsetAsync(ws + w.f.gG, 0, sizeof(float) * (size_t)I * K, st));
+    CY2P_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * sc.total, st));
+    CY2P_CUDA(cudaMemsetAsync(scal1, 0, sizeof(double) * ScalarOffsets(S, 1, S).total, st));
+    rc = lssm_run_forward(S, L, Le, N, I, restricted, theta_pi, theta_w, theta_E, theta_A, w, ws, st);
+    if (rc) return rc;
+    dispatch_data_pass(N, I, K, w.f, logE, (const float *)(ws + w.f.G), d_D, nullptr, (float *)(ws + w.f.split),
+                       (float *)(ws + w.f.gG), scal + sc.div, st);
+    const unsigned gN = (unsigned)((N + 127) / 128);
+    count_launch();
+    fhmm_node_pass_a<<<gN, 128, 0, st>>>(S, L, Le, N, logE, aux, X1, X2);
+    rc = cy2p_propagate_rows(plan, X1, Y1, S + L, 0, N, stream);
+    if (rc) return rc;
+    count_launch();
+    csr_times_small<<<(unsigned)(((int64_t)N * L + 255) / 256), 256, 0, st>>>(N, L, plan->d_indptr, plan->d_indices,
+                                                                             plan->d_data, X2, TP);
+    count_launch();
+    fhmm_node_pass_b<<<gN, 128, 0, st>>>(S, L, Le, N, logE, aux, X1, X2, Y1, scal, K);
+    count_launch();
+    fhmm_node_pass_c<<<gN, 128, 0, st>>>(S, L, Le, N, K, w.f.nsplit, logE, aux, X1, X2, Y1, TP,
+                                         (const float *)(ws + w.f.split), scal, w_excl, w_orth, w_tpm, d_gE);
+    count_launch();
+    fhmm_emission_grad_finish<<<(unsigned)(((int64_t)K * N + 255) / 256), 256, 0, st>>>(N, K, logE, scal + sc.rowsum,
+                                                                                       d_gE);
+    count_launch();
+    fhmm_ll_nodes<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(S, L, Le, N, I, logE, (const double *)(ws + w.f.row_lse),
+                                                               (double *)(ws + w.f.llv));
+    const int nparts = (N + 255) / 256;
+    count_launch();
+    lse_partials<<<nparts, 256, 0, st>>>(N, (const double *)(ws + w.f.llv), (double2 *)(ws + w.f.llpart));
+    count_launch();
+    lse_combine<<<1, 256, 0, st>>>(nparts, (const double2 *)(ws + w.f.llpart), scal + sc.ll);
+    // fold the lineage axis, then the single-chain backward (FHMM kernels with L = 1)
+    count_launch();
+    lssm_glue_backward<<<S, 256, 0, st>>>(S, L, I, restricted, K, (const float *)(ws + w.lsmall),
+                                          (const double *)(ws + w.f.Hlin), (const float *)(ws + w.f.gG), scal, aux,
+                                          w_sparse, w_excl, w_orth, w_tpm, (float *)(ws + w.gG1), scal1, d_gw, d_terms);
+    const int NB = (I + w.P1 - 1) / w.P1;
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_local1));
+    count_launch();
+    fhmm_bwd_local<<<NB, 32, w.smem_local1, st>>>(S, 1, I, w.P1, 1, S, (const float *)(ws + w.small1),
+                                                  (const float *)(ws + w.aux1), (const float *)(ws + w.gG1), scal1,
+                                                  (float *)(ws + w.f.gH));
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bwd1));
+    float *tmp = (float *)(ws + w.tmp);
+    count_launch();
+    fhmm_small_backward<<<1, 512, w.smem_bwd1, st>>>(S, 1, I, w.P1, 1, S, (const float *)(ws + w.small1),
+                                                     (const double *)(ws + w.f.Hlin), (const double *)(ws + w.Apow1),
+                                                     (const float *)(ws + w.aux1), (const float *)(ws + w.gG1), scal1,
+                                                     w_sparse, 0.f, 0.f, 0.f, (float *)(ws + w.f.gH), d_gpi, tmp,
+                                                     d_gA, tmp + 4);
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+int32_t cy2p_lssm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted, const float *theta_pi,
+                         const float *theta_w, const float *theta_E, const float *theta_A, const float *d_D,
+                         float *d_log_alpha, float *d_log_probs, float *d_log_beta, float *d_log_gamma,
+                         float *d_log_delta, float *d_psi, float *d_log_max, float *d_best_path, void *d_ws,
+                         size_t ws_bytes, void *stream) {
+    int32_t rc = check_dims(S, L, N, I, restricted);
+    if (rc) return rc;
+    CY2P_REQUIRE(theta_pi && theta_w && theta_E && theta_A && d_D, "null input");
+    CY2P_REQUIRE(d_log_alpha && d_log_probs && d_log_beta && d_log_gamma && d_log_delta && d_psi && d_log_max &&
+                     d_best_path, "null output");
+    CY2P_REQUIRE(S * L <= 512, "decoders need S*L <= 512");
+    const int Le = restricted ? 1 : L, K = S * Le;
+    const LssmWs w = lssm_layout(S, L, Le, N, I);
+    if ((rc = lssm_check_ws(w, d_ws, ws_bytes))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    rc = lssm_run_forward(S, L, Le, N, I, restricted, theta_pi, theta_w, theta_E, theta_A, w, ws, st);
+    if (rc) return rc;
+    const float *logE = (const float *)(ws + w.f.logE);
+    float *rowmax = (float *)(ws + w.f.gG);
+    float *bm = (float *)(ws + w.f.X1);
+    if ((size_t)I * K > (size_t)N * (S + L)) bm = (float *)(ws + w.f.split);
+    count_launch();
+    fhmm_row_max<<<K, 256, 0, st>>>(N, logE, rowmax);
+    count_launch();
+    fhmm_bmat<<<dim3(I, K), 256, 0, st>>>(N, K, d_D, logE, rowmax, bm);
+    float *small_exp = (float *)(ws + w.f.small), *Bexp = (float *)(ws + w.f.gH);  // both free on this path
+    count_launch();
+    lssm_expand_decode<<<64, 256, 0, st>>>(S, L, Le, I, (const float *)(ws + w.lsmall), bm, small_exp, Bexp);
+    const size_t smem = sizeof(float) * ((size_t)L * S * S + 2 * (size_t)S * L + 2 * L);
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_decode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    count_launch();
+    fhmm_decode_small<<<1, 512, smem, st>>>(S, L, L, I, small_exp, Bexp, d_log_alpha, d_log_probs, d_log_beta,
+                                            d_log_gamma, d_log_delta, d_psi, d_log_max, d_best_path);
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }

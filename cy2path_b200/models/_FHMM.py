@@ -19,6 +19,8 @@ class FHMM(torch.nn.Module):
     the CUDA device: there is no CPU execution path (``use_gpu`` is accepted for compatibility).
     """
 
+    _kind = "fhmm"  # selects the cy2p_<kind>_* entry points (LSSM overrides it)
+
     def __init__(self, num_states, num_chains, num_nodes, num_iters, restricted=True, use_gpu=False):
         super().__init__()
         self.num_nodes = num_nodes
@@ -47,7 +49,8 @@ class FHMM(torch.nn.Module):
         ``want_joint=False`` skips the I*S*L*N tensor (4 GB at S=10, L=4, N=50k, I=500)."""
         out = _lib.fhmm_forward(self.unnormalized_state_init, self.unnormalized_chain_weights,
                                 self.unnormalized_emission_matrix, self.unnormalized_transition_matrix,
-                                self.num_iters, self.restricted, want_pred=True, want_joint=want_joint)
+                                self.num_iters, self.restricted, want_pred=True, want_joint=want_joint,
+                                model=self._kind)
         self.log_state_init = out["log_pi"]
         self.log_chain_weights = out["log_w"]
         self.log_emission_matrix = out["log_E"]
@@ -59,7 +62,7 @@ class FHMM(torch.nn.Module):
     def _decode(self, D):
         out = _lib.fhmm_decode(self.unnormalized_state_init, self.unnormalized_chain_weights,
                                self.unnormalized_emission_matrix, self.unnormalized_transition_matrix,
-                               torch.as_tensor(D), self.restricted)
+                               torch.as_tensor(D), self.restricted, model=self._kind)
         log_transform_params(self)
         self.log_transition_matrix_ = self.log_transition_matrix
         return out

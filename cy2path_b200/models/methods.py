@@ -8,7 +8,8 @@ def log_transform_params(self):
     """reference methods.py:6-25: the four log_softmax normalisations, set as attributes."""
     out = _lib.fhmm_forward(self.unnormalized_state_init, self.unnormalized_chain_weights,
                             self.unnormalized_emission_matrix, self.unnormalized_transition_matrix,
-                            self.num_iters, self.restricted, want_pred=False, want_joint=False)
+                            self.num_iters, self.restricted, want_pred=False, want_joint=False,
+                            model=getattr(self, "_kind", "fhmm"))
     self.log_state_init = out["log_pi"]
     self.log_chain_weights = out["log_w"]
     self.log_emission_matrix = out["log_E"]
@@ -32,7 +33,7 @@ def compute_log_likelihood(self):
         plan = get_plan(self._eye)
     terms, _, _ = _lib.fhmm_loss_grad(plan, self.unnormalized_state_init.data, self.unnormalized_chain_weights.data,
                                       self.unnormalized_emission_matrix.data, self.unnormalized_transition_matrix.data,
-                                      zeros, self.restricted, (0.0, 0.0, 0.0, 0.0))
+                                      zeros, self.restricted, (0.0, 0.0, 0.0, 0.0), model=getattr(self, "_kind", "fhmm"))
     self.log_likelihood = terms[2].clone()
 
 

@@ -79,16 +79,18 @@ def train(self, D, TPM=None, num_epochs=300, sparsity_weight=1.0, exclusivity_we
     params = [self.unnormalized_state_init, self.unnormalized_chain_weights, self.unnormalized_emission_matrix,
               self.unnormalized_transition_matrix]
     weights = (sparsity_weight, exclusivity_weight, orthogonality_weight, TPM_weight)
+    kind = getattr(self, "_kind", "fhmm")  # the reference's trainer is shared by its model classes
     history = torch.empty((max(num_epochs, 1), 8), dtype=torch.float32, device=dev)
     bufs = None
     start_time = time.time()
     for epoch in range(num_epochs):
         # cy2p_fhmm_loss_grad overwrites every gradient entry, so there is nothing to zero (trainer.py:130 zero_grad)
         terms, grads, bufs = _lib.fhmm_loss_grad(plan, *[p.data for p in params], D, self.restricted, weights, out=bufs,
-                                                 terms=history[epoch])
+                                                 terms=history[epoch], model=kind)
         report = epoch % 100 == 99 or epoch <= 9
         if report:  # correlation of the (pre-step) prediction with the data, trainer.py:205-210
-            pred = _lib.fhmm_forward(*[p.data for p in params], self.num_iters, self.restricted, want_pred=True)["pred"]
+            pred = _lib.fhmm_forward(*[p.data for p in params], self.num_iters, self.restricted, want_pred=True,
+                                     model=kind)["pred"]
             out = torch.exp(pred)
             a = out - out.mean(1, keepdim=True)
             b = D - D.mean(1, keepdim=True)

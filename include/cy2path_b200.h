@@ -186,6 +186,30 @@ int32_t cy2p_fhmm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t res
                          float *d_log_delta, float *d_psi, float *d_log_max, float *d_best_path, void *d_ws,
                          size_t ws_bytes, void *stream);
 
+/* ---- K3b: latent state-space model with state-level lineage weights (LSSM) ----------------------
+ * Same call shapes as the FHMM entry points; replaces LSSM.forward_model (_LSSM.py:83-117), one epoch of
+ * trainer.train on an LSSM (trainer.py:134-196; the trainer is shared by the model classes) and
+ * LSSM.filtering / smoothing / viterbi (_LSSM.py:120-260). Parameter shapes differ:
+ *   theta_pi [S], theta_w [S][L], theta_E [S][Le][N], theta_A [S][S];  d_hidden [I][S];
+ *   d_small  out, [cy2p_lssm_small_floats(S,L)] floats: log_pi [S], log_w [S][L], log_A [S][S]
+ *   gradients d_gpi [S], d_gw [S][L], d_gE [S][Le][N], d_gA [S][S];  d_ws >= cy2p_lssm_ws_bytes(S,L,N,I) */
+size_t cy2p_lssm_ws_bytes(int32_t S, int32_t L, int32_t N, int32_t I);
+int32_t cy2p_lssm_small_floats(int32_t S, int32_t L);
+int32_t cy2p_lssm_forward(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted,
+                          const float *theta_pi, const float *theta_w, const float *theta_E,
+                          const float *theta_A, float *d_pred, float *d_hidden, float *d_joint,
+                          float *d_logE, float *d_small, void *d_ws, size_t ws_bytes, void *stream);
+int32_t cy2p_lssm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted,
+                            const float *theta_pi, const float *theta_w, const float *theta_E,
+                            const float *theta_A, const float *d_D, const float *h_weights,
+                            float *d_terms, float *d_gpi, float *d_gw, float *d_gE, float *d_gA,
+                            void *d_ws, size_t ws_bytes, void *stream);
+int32_t cy2p_lssm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted, const float *theta_pi,
+                         const float *theta_w, const float *theta_E, const float *theta_A, const float *d_D,
+                         float *d_log_alpha, float *d_log_probs, float *d_log_beta, float *d_log_gamma,
+                         float *d_log_delta, float *d_psi, float *d_log_max, float *d_best_path, void *d_ws,
+                         size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

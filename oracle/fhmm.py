@@ -46,6 +46,26 @@ def forward_model(theta_pi, theta_w, theta_E, theta_A, num_iters, want_joint=Tru
     return pred, (joint if want_joint else None), hidden, log_A_mix
 
 
+def lssm_forward_model(theta_pi, theta_w, theta_E, theta_A, num_iters, want_joint=True):
+    """reference: cy2path/models/_LSSM.py:83-117 (LSSM: one latent chain, state-level chain weights).
+
+    theta_pi [S], theta_w [S,L], theta_E [S,1|L,N], theta_A [S,S].
+    hidden[0] = log pi; hidden[t][s'] = lse_s(hidden[t-1][s] + log A[s, s'])            (:103-107)
+    joint[t, s, l, n] = log E[s, l', n] + log w[s, l] + hidden[t, s]                     (:98-111)
+    Returns pred [I,N], joint [I,S,L,N] (or None), hidden [I,S], log A [S,S]."""
+    log_pi = torch.log_softmax(theta_pi, dim=0)
+    log_w = torch.log_softmax(theta_w, dim=-1)
+    log_E = torch.log_softmax(theta_E, dim=-1)
+    log_A = torch.log_softmax(theta_A, dim=-1)
+    h = [log_pi]
+    for _ in range(1, num_iters):
+        h.append(LSE(h[-1].unsqueeze(-1) + log_A, dim=0))
+    hidden = torch.stack(h, 0)  # [I, S]
+    joint = (log_E + log_w.unsqueeze(-1)).unsqueeze(0) + hidden[:, :, None, None]
+    pred = LSE(LSE(joint, dim=1), dim=1)
+    return pred, (joint if want_joint else None), hidden, log_A
+
+
 def log_domain_mean(x, dim=0):
     """reference: cy2path/utils.py:139-145."""
     return LSE(x, dim) - math.log(x.shape[dim])
@@ -62,14 +82,18 @@ def _kl_batchmean(log_input, target):
     return torch.nn.functional.kl_div(log_input, target, reduction="batchmean", log_target=False)
 
 
-def loss_terms(theta_pi, theta_w, theta_E, theta_A, D, TPM, weights=(1.0, 0.1, 0.1, 0.0)):
+def loss_terms(theta_pi, theta_w, theta_E, theta_A, D, TPM, weights=(1.0, 0.1, 0.1, 0.0), model="fhmm"):
     """reference: cy2path/models/trainer.py:134-193 (one epoch's forward + loss).
 
     ``weights`` = (sparsity, exclusivity, orthogonality, TPM). TPM may be a dense [N,N] tensor or a
     torch sparse tensor. Returns dict of the scalar terms, 'loss', and the forward outputs."""
     I = D.shape[0]
-    S, L = theta_pi.shape
-    pred, joint, hidden, log_A_mix = forward_model(theta_pi, theta_w, theta_E, theta_A, I)
+    if model == "lssm":  # the trainer is shared between the model classes (trainer.py:134-196)
+        S, L = theta_w.shape
+        pred, joint, hidden, log_A_mix = lssm_forward_model(theta_pi, theta_w, theta_E, theta_A, I)
+    else:
+        S, L = theta_pi.shape
+        pred, joint, hidden, log_A_mix = forward_model(theta_pi, theta_w, theta_E, theta_A, I)
     sw, ew, ow, tw = weights
     out = {}
     out["divergence"] = _kl_batchmean(pred, D)  # trainer.py:139

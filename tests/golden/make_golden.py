@@ -69,7 +69,7 @@ def golden_chains(ref, name, n, k, seed, C, max_iter, variable_degree=False):
     print(name, idx.shape, states.shape)
 
 
-def golden_fhmm(ref, name, S, L, N, I, restricted, seed, k=6):
+def golden_fhmm(ref, name, S, L, N, I, restricted, seed, k=6, model_cls="FHMM"):
     g = knn_velocity_tpm(N, k=k, seed=seed)
     ad = adata_for(g, ref)
     init_p, _ = ref.utils.check_root_init(ad, init="root_cells")
@@ -77,8 +77,17 @@ def golden_fhmm(ref, name, S, L, N, I, restricted, seed, k=6):
     _, shm, _ = ref.sampling.iterate_state_probability(ad, init=init_p, stationary=stat, max_iter=I)
     D = torch.Tensor(shm)  # float32, as infer_dynamics.py:207-211
     TPM = torch.Tensor(g["T"].toarray())  # dense, as infer_dynamics.py:204
-    torch.manual_seed(seed)
-    model = ref.models.FHMM(S, L, N, I, restricted=restricted, use_gpu=False)
+    cls = getattr(ref.models, model_cls)
+
+    def make():
+        torch.manual_seed(seed)
+        m = cls(S, L, N, I, restricted=restricted, use_gpu=False)
+        if model_cls == "LSSM":  # the reference initialises the chain weights to ones (_LSSM.py:59-64);
+            with torch.no_grad():  # randomise them so the fixture exercises the weight gradient
+                m.unnormalized_chain_weights.copy_(torch.randn(S, L))
+        return m
+
+    model = make()
     params0 = {k_: v.detach().clone().numpy() for k_, v in model.state_dict().items()}
     with torch.no_grad():
         pred, joint, hidden = model.forward_model()
@@ -93,8 +102,7 @@ def golden_fhmm(ref, name, S, L, N, I, restricted, seed, k=6):
                  orthogonality=model.orthogonality_values[0], regularisation=model.regularisation_values[0],
                  exclusivity=(model.exclusivity_values[0] if L > 1 else np.nan))
     # three default-optimiser epochs from the same start (trainer drop-in trajectory)
-    torch.manual_seed(seed)
-    model2 = ref.models.FHMM(S, L, N, I, restricted=restricted, use_gpu=False)
+    model2 = make()
     model2.train(D, TPM=TPM, num_epochs=3)
     traj = np.array([model2.loss_values, model2.divergence_values, model2.likelihood_values,
                      model2.sparsity_values, model2.orthogonality_values,
@@ -117,14 +125,26 @@ def golden_fhmm(ref, name, S, L, N, I, restricted, seed, k=6):
 
 
 def main():
+    """``python make_golden.py [prefix ...]`` regenerates every fixture, or those whose file name starts with a prefix."""
+    import sys
+
     ref = ref_shim.load()
-    golden_msm(ref, "msm_small.npz", n=400, k=10, seed=11, max_iter=120)
-    golden_msm(ref, "msm_vardeg.npz", n=300, k=12, seed=12, max_iter=80, variable_degree=True, init="uniform")
-    golden_chains(ref, "chains_small.npz", n=400, k=10, seed=11, C=48, max_iter=60)
-    golden_chains(ref, "chains_wide.npz", n=300, k=40, seed=13, C=32, max_iter=40)  # W > 32: multi-chunk search
-    golden_fhmm(ref, "fhmm_restricted.npz", S=4, L=3, N=60, I=25, restricted=True, seed=21)
-    golden_fhmm(ref, "fhmm_unrestricted.npz", S=3, L=2, N=50, I=20, restricted=False, seed=22)
-    golden_fhmm(ref, "fhmm_single_chain.npz", S=5, L=1, N=40, I=15, restricted=True, seed=23)
+    jobs = [
+        (golden_msm, "msm_small.npz", dict(n=400, k=10, seed=11, max_iter=120)),
+        (golden_msm, "msm_vardeg.npz", dict(n=300, k=12, seed=12, max_iter=80, variable_degree=True, init="uniform")),
+        (golden_chains, "chains_small.npz", dict(n=400, k=10, seed=11, C=48, max_iter=60)),
+        (golden_chains, "chains_wide.npz", dict(n=300, k=40, seed=13, C=32, max_iter=40)),  # W > 32: multi-chunk search
+        (golden_fhmm, "fhmm_restricted.npz", dict(S=4, L=3, N=60, I=25, restricted=True, seed=21)),
+        (golden_fhmm, "fhmm_unrestricted.npz", dict(S=3, L=2, N=50, I=20, restricted=False, seed=22)),
+        (golden_fhmm, "fhmm_single_chain.npz", dict(S=5, L=1, N=40, I=15, restricted=True, seed=23)),
+        (golden_fhmm, "lssm_restricted.npz", dict(S=4, L=3, N=60, I=25, restricted=True, seed=31, model_cls="LSSM")),
+        (golden_fhmm, "lssm_unrestricted.npz", dict(S=3, L=2, N=50, I=20, restricted=False, seed=32, model_cls="LSSM")),
+        (golden_fhmm, "lssm_single_chain.npz", dict(S=5, L=1, N=40, I=15, restricted=True, seed=33, model_cls="LSSM")),
+    ]
+    for fn, name, kw in jobs:
+        if len(sys.argv) > 1 and not any(name.startswith(p) for p in sys.argv[1:]):
+            continue
+        fn(ref, name, **kw)
 
 
 if __name__ == "__main__":

@@ -16,18 +16,27 @@ NAMES = ("unnormalized_state_init", "unnormalized_chain_weights", "unnormalized_
          "unnormalized_transition_matrix")
 
 
-def _model_from(g):
-    from cy2path_b200.models import FHMM
+GOLDEN = ["fhmm_restricted.npz", "fhmm_unrestricted.npz", "fhmm_single_chain.npz",
+          "lssm_restricted.npz", "lssm_unrestricted.npz", "lssm_single_chain.npz"]  # LSSM: SURVEY §8 f-3
 
+
+def _cls(name):
+    from cy2path_b200 import models
+
+    return models.LSSM if name.startswith("lssm") else models.FHMM
+
+
+def _model_from(g, name="fhmm"):
+    FHMM = _cls(name)
     m = FHMM(int(g["S"]), int(g["L"]), int(g["N"]), int(g["I"]), restricted=bool(g["restricted"]), use_gpu=True)
     m.load_state_dict({k: torch.tensor(g[k]) for k in NAMES})
     return m
 
 
-@pytest.mark.parametrize("name", ["fhmm_restricted.npz", "fhmm_unrestricted.npz", "fhmm_single_chain.npz"])
+@pytest.mark.parametrize("name", GOLDEN)
 def test_forward_matches_reference_golden(golden, name):
     g = golden(name)
-    m = _model_from(g)
+    m = _model_from(g, name)
     pred, joint, hidden = m.forward_model()
     assert pred.shape == g["pred"].shape and joint.shape == g["joint"].shape and hidden.shape == g["hidden"].shape
     assert np.abs(pred.cpu().numpy() - g["pred"]).max() <= 1e-5
@@ -39,17 +48,17 @@ def test_forward_matches_reference_golden(golden, name):
     assert m.log_transition_matrix_.shape == g["unnormalized_transition_matrix"].shape
 
 
-@pytest.mark.parametrize("name", ["fhmm_restricted.npz", "fhmm_unrestricted.npz", "fhmm_single_chain.npz"])
+@pytest.mark.parametrize("name", GOLDEN)
 def test_loss_terms_and_gradients_match_reference_golden(golden, name):
     from cy2path_b200 import _lib
     from cy2path_b200.sampling import get_plan
 
     g = golden(name)
-    m = _model_from(g)
+    m = _model_from(g, name)
     plan = get_plan(g["T"])
     D = torch.tensor(g["D"]).cuda()
     terms, grads, _ = _lib.fhmm_loss_grad(plan, *[p.data for p in m.parameters()], D, bool(g["restricted"]),
-                                          tuple(g["weights"]))
+                                          tuple(g["weights"]), model=m._kind)
     t = dict(zip(_lib.TERM_NAMES, terms.cpu().numpy().tolist()))
     ref = dict(zip(g["term_names"].tolist(), g["term_values"].tolist()))
     for k in ("loss", "divergence", "sparsity", "orthogonality", "regularisation"):
@@ -63,13 +72,14 @@ def test_loss_terms_and_gradients_match_reference_golden(golden, name):
         assert np.abs(gq.cpu().numpy() - rg).max() <= 1e-5 + 1e-3 * np.abs(rg).max(), nme
 
 
+@pytest.mark.parametrize("kind", ["fhmm", "lssm"])
 @pytest.mark.parametrize("S,L,restricted,N,I", [(10, 4, True, 2000, 60), (5, 3, False, 1500, 40), (12, 2, True, 777, 33),
                                                  (3, 1, False, 300, 9)])
-def test_mid_size_vs_oracle_autograd(S, L, restricted, N, I):
+def test_mid_size_vs_oracle_autograd(S, L, restricted, N, I, kind):
     import scipy.sparse as sp
 
     from cy2path_b200 import _lib
-    from cy2path_b200.models import FHMM
+    FHMM = _cls(kind)
     from cy2path_b200.sampling import get_plan
     from cy2path_b200.synth import knn_velocity_tpm
 
@@ -80,12 +90,15 @@ def test_mid_size_vs_oracle_autograd(S, L, restricted, N, I):
     D = _lib.propagate(plan, x0, I, history_stride=1, want_final=False)["history"].contiguous()
     torch.manual_seed(7)
     m = FHMM(S, L, N, I, restricted=restricted, use_gpu=True)
+    if kind == "lssm":  # the LSSM starts from uniform chain weights (_LSSM.py:59-64); exercise a generic point
+        with torch.no_grad():
+            m.unnormalized_chain_weights.copy_(torch.randn(S, L))
     wts = (1.0, 0.1, 0.1, 0.05)
-    terms, grads, _ = _lib.fhmm_loss_grad(plan, *[p.data for p in m.parameters()], D, restricted, wts)
+    terms, grads, _ = _lib.fhmm_loss_grad(plan, *[p.data for p in m.parameters()], D, restricted, wts, model=kind)
     th = [p.detach().cpu().clone().requires_grad_(True) for p in m.parameters()]
     coo = sp.coo_matrix(T)
     Tt = torch.sparse_coo_tensor(np.vstack([coo.row, coo.col]), coo.data.astype(np.float32), (N, N)).coalesce()
-    ref = ofhmm.loss_terms(*th, D.cpu(), Tt, weights=wts)
+    ref = ofhmm.loss_terms(*th, D.cpu(), Tt, weights=wts, model=kind)
     ref["loss"].backward()
     t = dict(zip(_lib.TERM_NAMES, terms.cpu().numpy().tolist()))
     for k in ("loss", "divergence", "sparsity", "orthogonality", "regularisation"):
@@ -101,9 +114,10 @@ def test_mid_size_vs_oracle_autograd(S, L, restricted, N, I):
     assert np.abs(pred.cpu().numpy() - ref["pred"].detach().numpy()).max() <= 2e-5
 
 
-def test_trainer_drop_in(golden):
-    g = golden("fhmm_restricted.npz")
-    m = _model_from(g)
+@pytest.mark.parametrize("name", ["fhmm_restricted.npz", "lssm_restricted.npz"])
+def test_trainer_drop_in(golden, name):
+    g = golden(name)
+    m = _model_from(g, name)
     D = torch.tensor(g["D"])
     m.train(D, TPM=g["T"], num_epochs=3)  # default weights, default RMSprop(lr=0.2)
     assert m.elapsed_epochs == 3 and len(m.loss_values) == 3 and len(m.exclusivity_values) == 3
@@ -139,11 +153,10 @@ def test_training_reduces_loss_at_moderate_size():
     assert m.loss_values[-1] < 0.7 * m.loss_values[0]
 
 
-@pytest.mark.parametrize("name", ["fhmm_restricted.npz", "fhmm_unrestricted.npz", "fhmm_single_chain.npz"])
+@pytest.mark.parametrize("name", GOLDEN)
 def test_decoders_match_reference_golden(golden, name):
     """filtering / smoothing / viterbi on the reference's 3-epoch-trained parameters."""
-    from cy2path_b200.models import FHMM
-
+    FHMM = _cls(name)
     g = golden(name)
     m = FHMM(int(g["S"]), int(g["L"]), int(g["N"]), int(g["I"]), restricted=bool(g["restricted"]), use_gpu=True)
     m.load_state_dict({k: torch.tensor(g["after3_" + k]) for k in NAMES})

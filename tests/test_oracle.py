@@ -74,13 +74,16 @@ def _params(g):
                                          "unnormalized_emission_matrix", "unnormalized_transition_matrix")]
 
 
-@pytest.mark.parametrize("name", ["fhmm_restricted.npz", "fhmm_unrestricted.npz", "fhmm_single_chain.npz"])
+@pytest.mark.parametrize("name", ["fhmm_restricted.npz", "fhmm_unrestricted.npz", "fhmm_single_chain.npz",
+                                  "lssm_restricted.npz", "lssm_unrestricted.npz", "lssm_single_chain.npz"])
 def test_fhmm_oracle_matches_reference(golden, name):
+    """FHMM and LSSM (the same trainer drives both, reference trainer.py:134-196)."""
     g = golden(name)
+    kind = name.split("_")[0]
     th = [t.requires_grad_(True) for t in _params(g)]
     D = torch.tensor(g["D"])
     TPM = torch.tensor(g["T"].toarray())
-    out = ofhmm.loss_terms(*th, D, TPM, weights=tuple(g["weights"]))
+    out = ofhmm.loss_terms(*th, D, TPM, weights=tuple(g["weights"]), model=kind)
     assert torch.allclose(out["pred"], torch.tensor(g["pred"]), atol=1e-5, rtol=0)
     assert torch.allclose(out["hidden"], torch.tensor(g["hidden"]), atol=1e-5, rtol=0)
     assert torch.allclose(out["joint"], torch.tensor(g["joint"]), atol=1e-5, rtol=0)
