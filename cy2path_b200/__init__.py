@@ -12,12 +12,12 @@ __version__ = "0.1.0"
 
 __all__ = [
     "iterate_state_probability", "sample_state_probability", "check_convergence_criteria", "propagate_batch",
-    "extract_nonzero_entries", "iterate_markov_chain", "sample_markov_chains", "FHMM", "LSSM",
+    "extract_nonzero_entries", "iterate_markov_chain", "sample_markov_chains", "FHMM", "LSSM", "NSSM",
 ]
 
 
 def __getattr__(name):  # lazy: torch.nn is only imported when the model is used
-    if name in ("FHMM", "LSSM"):
+    if name in ("FHMM", "LSSM", "NSSM"):
         from . import models
 
         return getattr(models, name)

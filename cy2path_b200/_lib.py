@@ -25,7 +25,8 @@ SYMBOLS = [
     "cy2p_propagate_rows_allgather_f64", "cy2p_enable_peer_access", "cy2p_cdf_build",
     "cy2p_sample_chains", "cy2p_chain_history", "cy2p_fhmm_ws_bytes", "cy2p_fhmm_small_floats",
     "cy2p_fhmm_forward", "cy2p_fhmm_loss_grad", "cy2p_fhmm_decode", "cy2p_lssm_ws_bytes", "cy2p_lssm_small_floats",
-    "cy2p_lssm_forward", "cy2p_lssm_loss_grad", "cy2p_lssm_decode",
+    "cy2p_lssm_forward", "cy2p_lssm_loss_grad", "cy2p_lssm_decode", "cy2p_nssm_ws_bytes", "cy2p_nssm_forward",
+    "cy2p_nssm_loss_grad", "cy2p_nssm_decode",
 ]
 
 _lib = None
@@ -90,12 +91,18 @@ def load():
         lib.cy2p_lssm_forward.argtypes = lib.cy2p_fhmm_forward.argtypes
         lib.cy2p_lssm_loss_grad.argtypes = lib.cy2p_fhmm_loss_grad.argtypes
         lib.cy2p_lssm_decode.argtypes = lib.cy2p_fhmm_decode.argtypes
+    if hasattr(lib, "cy2p_nssm_forward"):
+        lib.cy2p_nssm_ws_bytes.argtypes = lib.cy2p_fhmm_ws_bytes.argtypes
+        lib.cy2p_nssm_ws_bytes.restype = _sz
+        lib.cy2p_nssm_forward.argtypes = [_i32] * 5 + [_vp] * 11 + [_sz, _vp]
+        lib.cy2p_nssm_loss_grad.argtypes = lib.cy2p_fhmm_loss_grad.argtypes
+        lib.cy2p_nssm_decode.argtypes = lib.cy2p_fhmm_decode.argtypes
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and name not in ("cy2p_last_error", "cy2p_propagate_ws_bytes", "cy2p_fhmm_ws_bytes",
                                            "cy2p_fhmm_small_floats", "cy2p_abi_version", "cy2p_launch_count",
                                            "cy2p_propagate_f64_ws_bytes", "cy2p_lssm_ws_bytes",
-                                           "cy2p_lssm_small_floats"):
+                                           "cy2p_lssm_small_floats", "cy2p_nssm_ws_bytes"):
             fn.restype = _i32
     _lib = lib
     return lib
@@ -235,14 +242,17 @@ def _model_dims(model, theta_pi, theta_w):
         return int(theta_pi.shape[0]), int(theta_pi.shape[1])
     if model == "lssm":
         return int(theta_w.shape[0]), int(theta_w.shape[1])
-    raise ValueError("model must be 'fhmm' or 'lssm'")
+    if model == "nssm":  # theta_pi [S], theta_w [1|S, N, L]
+        return int(theta_pi.shape[0]), int(theta_w.shape[-1])
+    raise ValueError("model must be 'fhmm', 'lssm' or 'nssm'")
 
 
 def _fhmm_ws(S, L, N, I, dev, model="fhmm"):
     torch = _torch()
     nbytes = getattr(load(), "cy2p_%s_ws_bytes" % model)(S, L, N, I)
     if nbytes == 0:
-        raise ValueError("unsupported model size (supported: S <= 32, L <= 16, S*(1 if restricted else L) <= 64)")
+        raise ValueError("unsupported model size (supported: S <= 32, L <= 16, S*(1 if restricted else L) <= 64; "
+                         "NSSM: S*L <= 64)")
     return torch.empty(nbytes, dtype=torch.uint8, device=dev), nbytes
 
 
@@ -254,10 +264,24 @@ def fhmm_forward(theta_pi, theta_w, theta_E, theta_A, num_iters, restricted, wan
     torch = _torch()
     lib = load()
     S, L = _model_dims(model, theta_pi, theta_w)
-    Le, N = theta_E.shape[1], theta_E.shape[2]
     I = int(num_iters)
     dev = theta_pi.device
     tp, tw, tE, tA = (t.detach().contiguous().float() for t in (theta_pi, theta_w, theta_E, theta_A))
+    if model == "nssm":
+        N = theta_E.shape[1]
+        with torch.cuda.device(dev):
+            ws, nbytes = _fhmm_ws(S, L, N, I, dev, model)
+            f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)  # noqa: E731
+            pred = f(I, N) if want_pred else None
+            hidden, joint = f(I, S), (f(I, S, L, N) if want_joint else None)
+            logE, logcw, small = f(S, N), f(*tw.shape), f(lib.cy2p_lssm_small_floats(S, L))
+            check(lib.cy2p_nssm_forward(S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE), ptr(tA), ptr(pred),
+                                        ptr(hidden), ptr(joint), ptr(logE), ptr(logcw), ptr(small), ptr(ws), nbytes,
+                                        stream_ptr(dev)))
+        return {"pred": pred, "hidden": hidden, "joint": joint, "log_E": logE, "log_pi": small[:S], "log_w": logcw,
+                "log_r": small[S:S + S * L].view(S, L), "log_A": small[S + S * L:].view(S, S),
+                "log_A_mix": small[S + S * L:].view(S, S)}
+    Le, N = theta_E.shape[1], theta_E.shape[2]
     with torch.cuda.device(dev):
         ws, nbytes = _fhmm_ws(S, L, N, I, dev, model)
         pred = torch.empty((I, N), dtype=torch.float32, device=dev) if want_pred else None
@@ -291,7 +315,7 @@ def fhmm_loss_grad(plan, theta_pi, theta_w, theta_E, theta_A, D, restricted, wei
     torch = _torch()
     lib = load()
     S, L = _model_dims(model, theta_pi, theta_w)
-    N = theta_E.shape[2]
+    N = theta_E.shape[-1]
     I = int(D.shape[0])
     dev = theta_pi.device
     tp, tw, tE, tA = (t.detach().contiguous() for t in (theta_pi, theta_w, theta_E, theta_A))
@@ -317,7 +341,7 @@ def fhmm_decode(theta_pi, theta_w, theta_E, theta_A, D, restricted, model="fhmm"
     torch = _torch()
     lib = load()
     S, L = _model_dims(model, theta_pi, theta_w)
-    N = theta_E.shape[2]
+    N = theta_E.shape[-1]
     I = int(D.shape[0])
     dev = theta_pi.device
     tp, tw, tE, tA = (t.detach().contiguous().float() for t in (theta_pi, theta_w, theta_E, theta_A))

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(256) emission_softmax_partials(int N, const fl
 
 __global__ void __launch_bounds__(256) emission_softmax_write(int N, const float *__restrict__ theta,
                                                               const float2 *__restrict__ partials,
-                                                              float *__restrict__ logE, double *__restrict__ row_sum) {
+                                                              float *__restrict__ logE, double *__restrict__ row_sum,
+                                                              float *__restrict__ row_lse_out = nullptr) {
     const int row = blockIdx.x, chunk = blockIdx.y, nchunks = gridDim.y;
     float m = -INFINITY;
     for (int c = 0; c < nchunks; ++c) m = fmaxf(m, partials[row * nchunks + c].x);
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256) emission_softmax_write(int N, const float
         z += (double)pz.y * (double)expf(pz.x - m);
     }
     const float lse = m + (float)log(z);
+    if (row_lse_out && chunk == 0 && threadIdx.x == 0) row_lse_out[row] = lse;
     const float *x = theta + (size_t)row * N;
     float *y = logE + (size_t)row * N;
     const int i0 = chunk * kSoftmaxChunk, i1 = min(N, i0 + kSoftmaxChunk);
@@ -1248,7 +1250,7 @@ struct LssmSmallOffsets {
 };
 
 __global__ void __launch_bounds__(512)
-lssm_mix_forward(int S, int L, int I, int restricted, int KP, const float *__restrict__ theta_w,
+lssm_mix_forward(int S, int L, int I, int restricted, int KP, int w_is_log, const float *__restrict__ theta_w,
                  const float *__restrict__ small1, const float *__restrict__ aux1, const double *__restrict__ Hlin1,
                  float *__restrict__ lsmall, float *__restrict__ G, float *__restrict__ aux) {
     const SmallOffsets so1(S, 1);
@@ -1262,7 +1264,7 @@ lssm_mix_forward(int S, int L, int I, int restricted, int KP, const float *__res
         for (int l = 0; l < L; ++l) m = fmaxf(m, x[l]);
         float z = 0.f;
         for (int l = 0; l < L; ++l) z += expf(x[l] - m);
-        const float lse = m + logf(z);
+        const float lse = w_is_log ? 0.f : m + logf(z);  // NSSM passes log r[s,l], already normalised over l
         for (int l = 0; l < L; ++l) {
             s_logw[s * L + l] = x[l] - lse;
             lsmall[lo.log_w + s * L + l] = x[l] - lse;
@@ -1321,7 +1323,7 @@ __global__ void lssm_joint_kernel(int S, int L, int Le, int N, int I, const floa
 // grid = S CTAs (one latent state each). Folds the lineage axis of dLoss/dG and dLoss/dlogC onto the single chain
 // and finishes the theta_w gradient; CTA 0 writes the 8 scalars.
 __global__ void __launch_bounds__(256)
-lssm_glue_backward(int S, int L, int I, int restricted, int K, const float *__restrict__ lsmall,
+lssm_glue_backward(int S, int L, int I, int restricted, int K, int raw_w, const float *__restrict__ lsmall,
                    const double *__restrict__ Hlin1, const float *__restrict__ gG, const double *__restrict__ scal,
                    const float *__restrict__ aux, float w_sparse, float w_excl, float w_orth, float w_tpm,
                    float *__restrict__ gG1, double *__restrict__ scal1, float *__restrict__ g_w,
@@ -1371,7 +1373,8 @@ lssm_glue_backward(int S, int L, int I, int restricted, int K, const float *__re
             tot += glw[l];
             gc += glc;
         }
-        for (int l = 0; l < L; ++l) g_w[s * L + l] = glw[l] - s_w[l] * tot;
+        // raw_w: dLoss/dlog w itself (the NSSM chains it through log r), else the softmax Jacobian of theta_w
+        for (int l = 0; l < L; ++l) g_w[s * L + l] = raw_w ? glw[l] : glw[l] - s_w[l] * tot;
         scal1[sc1.glogC + s] = gc;
         if (s == 0) write_terms(S, L, K, scal, aux[ao.sparsity], w_sparse, w_excl, w_orth, w_tpm, terms);
     }
@@ -1393,6 +1396,98 @@ __global__ void lssm_expand_decode(int S, int L, int Le, int I, const float *__r
         const int t = i / SL, e = i % SL, s = e / L, l = e % L;
         Bexp[i] = Bmat[(size_t)t * K + s * Le + (Le == 1 ? 0 : l)] + lsmall[lo.log_w + e];
     }
+}
+
+// --------------------------------------------------------------------------------------------------
+// NSSM (reference models/_NSSM.py:7-118): one latent chain with NODE-level lineage weights,
+//     joint[t,s,l,n] = logE[s,n] + log cw[s',n,l] + hidden[t,s]       (s' = 0 when the weights are shared by states).
+// Written as Etil[s,l,n] = E[s,n] cw[s',n,l] = r[s,l] Ehat[s,l,n] with Ehat rows normalised over n and
+// r[s,l] = sum_n Etil[s,l,n]  (sum_l r[s,l] = 1), this is the unrestricted LSSM with emission Ehat and lineage
+// weights r, so the LSSM path runs unchanged on (log Ehat, log r); the two kernels below build those inputs and
+// chain the gradients back to theta_E [S][N] and theta_cw [Sc][N][L].
+__global__ void __launch_bounds__(128)
+nssm_build(int S, int L, int Sc, int N, const float *__restrict__ theta_cw, const float *__restrict__ logE0,
+           float *__restrict__ logcw, float *__restrict__ Etil) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    for (int sc = 0; sc < Sc; ++sc) {
+        const float *x = theta_cw + ((size_t)sc * N + n) * L;
+        float v[kMaxL], m = -INFINITY;
+#pragma unroll
+        for (int l = 0; l < kMaxL; ++l)
+            if (l < L) {
+                v[l] = x[l];
+                m = fmaxf(m, v[l]);
+            }
+        float z = 0.f;
+#pragma unroll
+        for (int l = 0; l < kMaxL; ++l)
+            if (l < L) z += expf(v[l] - m);
+        const float lse = m + logf(z);
+#pragma unroll
+        for (int l = 0; l < kMaxL; ++l)
+            if (l < L) {
+                v[l] -= lse;  // log_softmax(theta_cw, dim=-1)  (methods.py:12-14)
+                logcw[((size_t)sc * N + n) * L + l] = v[l];
+            }
+        const int s_lo = Sc == 1 ? 0 : sc, s_hi = Sc == 1 ? S : sc + 1;
+        for (int s = s_lo; s < s_hi; ++s) {
+            const float e = logE0[(size_t)s * N + n];
+#pragma unroll
+            for (int l = 0; l < kMaxL; ++l)
+                if (l < L) Etil[(size_t)(s * L + l) * N + n] = e + v[l];
+        }
+    }
+}
+
+// gEt[k][n] = dLoss/dlog Ehat[k][n] (from the LSSM node pass), glw[k] = dLoss/dlog r[k], rowsum[k] = sum_n gEt[k][n].
+// dLoss/dlog Etil[k][n] = gEt[k][n] + Ehat[k][n] (glw[k] - rowsum[k]); its sums over l and over s are the gradients
+// w.r.t. logE[s][n] and log cw[s'][n][l]; the weights' softmax Jacobian is applied here, the emission's afterwards.
+__global__ void __launch_bounds__(128)
+nssm_backward_nodes(int S, int L, int Sc, int N, const float *__restrict__ gEt, const float *__restrict__ logEhat,
+                    const float *__restrict__ glw, const double *__restrict__ rowsum, const float *__restrict__ logcw,
+                    float *__restrict__ gE0, double *__restrict__ rowsum0, float *__restrict__ g_cw) {
+    __shared__ float s_coef[kMaxK];
+    __shared__ double s_acc[kMaxS];
+    for (int k = threadIdx.x; k < S * L; k += blockDim.x) s_coef[k] = glw[k] - (float)rowsum[k];
+    for (int k = threadIdx.x; k < S; k += blockDim.x) s_acc[k] = 0.0;
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = n < N;
+    const int nn = ok ? n : 0, lane = threadIdx.x & 31;
+    float gcw[kMaxL];
+#pragma unroll
+    for (int l = 0; l < kMaxL; ++l) gcw[l] = 0.f;
+    for (int s = 0; s < S; ++s) {
+        float ge = 0.f;
+#pragma unroll
+        for (int l = 0; l < kMaxL; ++l)
+            if (l < L) {
+                const size_t idx = (size_t)(s * L + l) * N + nn;
+                const float gt = gEt[idx] + expf(logEhat[idx]) * s_coef[s * L + l];
+                ge += gt;
+                gcw[l] += gt;
+            }
+        if (ok) gE0[(size_t)s * N + n] = ge;
+        const float rs = warp_sum(ok ? ge : 0.f);
+        if (lane == 0) atomicAdd(&s_acc[s], (double)rs);
+        if (Sc > 1 || s == S - 1) {  // softmax Jacobian of the weights of (s', n)
+            const int sc = Sc > 1 ? s : 0;
+            float tot = 0.f;
+#pragma unroll
+            for (int l = 0; l < kMaxL; ++l)
+                if (l < L) tot += gcw[l];
+#pragma unroll
+            for (int l = 0; l < kMaxL; ++l)
+                if (l < L) {
+                    const size_t idx = ((size_t)sc * N + nn) * L + l;
+                    if (ok) g_cw[idx] = gcw[l] - expf(logcw[idx]) * tot;
+                    gcw[l] = 0.f;
+                }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < S; k += blockDim.x) atomicAdd(&rowsum0[k], s_acc[k]);
 }
 
 }  // namespace cy2p
@@ -1586,9 +1681,11 @@ int32_t lssm_check_ws(const LssmWs &w, const void *d_ws, size_t ws_bytes) {
     return CY2P_OK;
 }
 
+// prenorm: logE (in the work space) and theta_w = log w are already normalised (the NSSM path)
 int32_t lssm_run_forward(int S, int L, int Le, int N, int I, int restricted, const float *theta_pi, const float *theta_w,
-                         const float *theta_E, const float *theta_A, const LssmWs &w, char *ws, cudaStream_t st) {
-    int32_t rc = run_emission(S * Le, N, theta_E, w.f, ws, st);
+                         const float *theta_E, const float *theta_A, const LssmWs &w, char *ws, cudaStream_t st,
+                         int prenorm = 0) {
+    int32_t rc = prenorm ? CY2P_OK : run_emission(S * Le, N, theta_E, w.f, ws, st);
     if (rc) return rc;
     if (w.smem_fwd1 > 220 * 1024 || w.smem_bwd1 > 220 * 1024) {
         set_error("model too large for the one-CTA recurrence kernels (S=%d, I=%d)", S, I);
@@ -1602,11 +1699,136 @@ int32_t lssm_run_forward(int S, int L, int Le, int N, int I, int restricted, con
                                                     (float *)(ws + w.G1), (float *)(ws + w.aux1),
                                                     (double *)(ws + w.f.Hlin), (double *)(ws + w.Apow1));
     count_launch();
-    lssm_mix_forward<<<1, 512, 0, st>>>(S, L, I, restricted, w.f.KP, theta_w, (const float *)(ws + w.small1),
+    lssm_mix_forward<<<1, 512, 0, st>>>(S, L, I, restricted, w.f.KP, prenorm, theta_w, (const float *)(ws + w.small1),
                                         (const float *)(ws + w.aux1), (const double *)(ws + w.f.Hlin),
                                         (float *)(ws + w.lsmall), (float *)(ws + w.f.G), (float *)(ws + w.f.aux));
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
+}
+
+// Everything after the forward pass of one LSSM epoch: the pass over D, the node passes, the log-likelihood, the
+// lineage fold and the single-chain backward. raw = 1 (NSSM): d_gE / d_gw receive dLoss/dlogE and dLoss/dlog w.
+int32_t lssm_loss_core(cy2p_plan *plan, int S, int L, int Le, int N, int I, int restricted, const LssmWs &w,
+                       char *ws, const float *d_D, const float *h_weights, float *d_terms, float *d_gpi,
+                       float *d_gw, float *d_gE, float *d_gA, int raw, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = S * Le;
+    int32_t rc;
+    const float w_sparse = h_weights[0], w_excl = h_weights[1], w_orth = h_weights[2], w_tpm = h_weights[3];
+    const ScalarOffsets sc(S, L, K);
+    float *logE = (float *)(ws + w.f.logE);
+    double *scal = (double *)(ws + w.f.scal), *scal1 = (double *)(ws + w.scal1);
+    const float *aux = (const float *)(ws + w.f.aux);
+    float *X1 = (float *)(ws + w.f.X1), *X2 = (float *)(ws + w.f.X2), *Y1 = (float *)(ws + w.f.Y1),
+          *TP = (float *)(ws + w.f.TP);
+    dispatch_data_pass(N, I, K, w.f, logE, (const float *)(ws + w.f.G), d_D, nullptr, (float *)(ws + w.f.split),
+                       (float *)(ws + w.f.gG), scal + sc.div, st);
+    const unsigned gN = (unsigned)((N + 127) / 128);
+    count_launch();
+    fhmm_node_pass_a<<<gN, 128, 0, st>>>(S, L, Le, N, logE, aux, X1, X2);
+    rc = cy2p_propagate_rows(plan, X1, Y1, S + L, 0, N, stream);
+    if (rc) return rc;
+    count_launch();
+    csr_times_small<<<(unsigned)(((int64_t)N * L + 255) / 256), 256, 0, st>>>(N, L, plan->d_indptr, plan->d_indices,
+                                                                             plan->d_data, X2, TP);
+    count_launch();
+    fhmm_node_pass_b<<<gN, 128, 0, st>>>(S, L, Le, N, logE, aux, X1, X2, Y1, scal, K);
+    count_launch();
+    fhmm_node_pass_c<<<gN, 128, 0, st>>>(S, L, Le, N, K, w.f.nsplit, logE, aux, X1, X2, Y1, TP,
+                                         (const float *)(ws + w.f.split), scal, w_excl, w_orth, w_tpm, d_gE);
+    if (!raw) {  // softmax Jacobian of the emission rows (the NSSM chains dLoss/dlogE itself)
+        count_launch();
+        fhmm_emission_grad_finish<<<(unsigned)(((int64_t)K * N + 255) / 256), 256, 0, st>>>(N, K, logE,
+                                                                                           scal + sc.rowsum, d_gE);
+    }
+    count_launch();
+    fhmm_ll_nodes<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(S, L, Le, N, I, logE, (const double *)(ws + w.f.row_lse),
+                                                               (double *)(ws + w.f.llv));
+    const int nparts = (N + 255) / 256;
+    count_launch();
+    lse_partials<<<nparts, 256, 0, st>>>(N, (const double *)(ws + w.f.llv), (double2 *)(ws + w.f.llpart));
+    count_launch();
+    lse_combine<<<1, 256, 0, st>>>(nparts, (const double2 *)(ws + w.f.llpart), scal + sc.ll);
+    // fold the lineage axis, then the single-chain backward (FHMM kernels with L = 1)
+    count_launch();
+    lssm_glue_backward<<<S, 256, 0, st>>>(S, L, I, restricted, K, raw, (const float *)(ws + w.lsmall),
+                                          (const double *)(ws + w.f.Hlin), (const float *)(ws + w.f.gG), scal, aux,
+                                          w_sparse, w_excl, w_orth, w_tpm, (float *)(ws + w.gG1), scal1, d_gw, d_terms);
+    const int NB = (I + w.P1 - 1) / w.P1;
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_local1));
+    count_launch();
+    fhmm_bwd_local<<<NB, 32, w.smem_local1, st>>>(S, 1, I, w.P1, 1, S, (const float *)(ws + w.small1),
+                                                  (const float *)(ws + w.aux1), (const float *)(ws + w.gG1), scal1,
+                                                  (float *)(ws + w.f.gH));
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bwd1));
+    float *tmp = (float *)(ws + w.tmp);
+    count_launch();
+    fhmm_small_backward<<<1, 512, w.smem_bwd1, st>>>(S, 1, I, w.P1, 1, S, (const float *)(ws + w.small1),
+                                                     (const double *)(ws + w.f.Hlin), (const double *)(ws + w.Apow1),
+                                                     (const float *)(ws + w.aux1), (const float *)(ws + w.gG1), scal1,
+                                                     w_sparse, 0.f, 0.f, 0.f, (float *)(ws + w.f.gH), d_gpi, tmp,
+                                                     d_gA, tmp + 4);
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+// ---- NSSM: the unrestricted LSSM work space plus the node-level pieces
+struct NssmWs {
+    LssmWs l;
+    size_t logE0, rowsum0, logcw, logr, gEt, glw, total;
+};
+
+NssmWs nssm_layout(int S, int L, int Sc, int N, int I) {
+    NssmWs w;
+    w.l = lssm_layout(S, L, L, N, I);
+    size_t off = w.l.total;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = up(off + bytes);
+        return o;
+    };
+    w.logE0 = take(sizeof(float) * (size_t)S * N);
+    w.rowsum0 = take(sizeof(double) * 2 * S);  // [0,S): sum exp(logE0) of the softmax, [S,2S): gradient row sums
+    w.logcw = take(sizeof(float) * (size_t)Sc * N * L);
+    w.logr = take(sizeof(float) * S * L);
+    w.gEt = take(sizeof(float) * (size_t)S * L * N);  // Etil on the way in, dLoss/dlog Ehat on the way back
+    w.glw = take(sizeof(float) * S * L);
+    w.total = off;
+    return w;
+}
+
+int32_t nssm_check(int S, int L, int N, int I, const NssmWs &w, const void *d_ws, size_t ws_bytes) {
+    int32_t rc = check_dims(S, L, N, I, 0);  // the effective emission has S*L rows
+    if (rc) return rc;
+    if (!d_ws || ws_bytes < w.total || ((uintptr_t)d_ws & 255)) {
+        set_error("work space too small or misaligned: need %zu bytes, 256-byte aligned", w.total);
+        return CY2P_ERR_WORKSPACE;
+    }
+    return CY2P_OK;
+}
+
+// log Ehat -> l.f.logE, log r -> logr, log E -> logE0, log cw -> logcw, then the LSSM forward on them
+int32_t nssm_run_forward(int S, int L, int Sc, int N, int I, const float *theta_pi, const float *theta_cw,
+                         const float *theta_E, const float *theta_A, const NssmWs &w, char *ws, cudaStream_t st) {
+    const int K = S * L, nchunks = (N + kSoftmaxChunk - 1) / kSoftmaxChunk;
+    float2 *partials = (float2 *)(ws + w.l.f.partials);
+    CY2P_CUDA(cudaMemsetAsync(ws + w.rowsum0, 0, sizeof(double) * 2 * S, st));
+    CY2P_CUDA(cudaMemsetAsync(ws + w.l.f.row_lse, 0, sizeof(double) * K, st));
+    count_launch();
+    emission_softmax_partials<<<dim3(S, nchunks), 256, 0, st>>>(N, theta_E, partials);
+    count_launch();
+    emission_softmax_write<<<dim3(S, nchunks), 256, 0, st>>>(N, theta_E, partials, (float *)(ws + w.logE0),
+                                                              (double *)(ws + w.rowsum0));
+    count_launch();
+    nssm_build<<<(N + 127) / 128, 128, 0, st>>>(S, L, Sc, N, theta_cw, (const float *)(ws + w.logE0),
+                                                (float *)(ws + w.logcw), (float *)(ws + w.gEt));
+    count_launch();
+    emission_softmax_partials<<<dim3(K, nchunks), 256, 0, st>>>(N, (const float *)(ws + w.gEt), partials);
+    count_launch();
+    emission_softmax_write<<<dim3(K, nchunks), 256, 0, st>>>(N, (const float *)(ws + w.gEt), partials,
+                                                              (float *)(ws + w.l.f.logE), (double *)(ws + w.l.f.row_lse),
+                                                              (float *)(ws + w.logr));
+    return lssm_run_forward(S, L, L, N, I, 0, theta_pi, (const float *)(ws + w.logr), nullptr, theta_A, w.l, ws, st, 1);
 }
 
 }  // namespace
@@ -1845,66 +2067,13 @@ int32_t cy2p_lssm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
     cudaStream_t st = (cudaStream_t)stream;
     CY2P_CUDA(cudaSetDevice(plan->device));
     char *ws = (char *)d_ws;
-    const float w_sparse = h_weights[0], w_excl = h_weights[1], w_orth = h_weights[2], w_tpm = h_weights[3];
-    const ScalarOffsets sc(S, L, K);
-    float *logE = (float *)(ws + w.f.logE);
-    double *scal = (double *)(ws + w.f.scal), *scal1 = (double *)(ws + w.scal1);
-    const float *aux = (const float *)(ws + w.f.aux);
-    float *X1 = (float *)(ws + w.f.X1), *X2 = (float *)(ws + w.f.X2), *Y1 = (float *)(ws + w.f.Y1),
-          *TP = (float *)(ws + w.f.TP);
-
     CY2P_CUDA(cudaMemsetAsync(ws + w.f.gG, 0, sizeof(float) * (size_t)I * K, st));
-    CY2P_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * sc.total, st));
-    CY2P_CUDA(cudaMemsetAsync(scal1, 0, sizeof(double) * ScalarOffsets(S, 1, S).total, st));
+    CY2P_CUDA(cudaMemsetAsync(ws + w.f.scal, 0, sizeof(double) * ScalarOffsets(S, L, K).total, st));
+    CY2P_CUDA(cudaMemsetAsync(ws + w.scal1, 0, sizeof(double) * ScalarOffsets(S, 1, S).total, st));
     rc = lssm_run_forward(S, L, Le, N, I, restricted, theta_pi, theta_w, theta_E, theta_A, w, ws, st);
     if (rc) return rc;
-    dispatch_data_pass(N, I, K, w.f, logE, (const float *)(ws + w.f.G), d_D, nullptr, (float *)(ws + w.f.split),
-                       (float *)(ws + w.f.gG), scal + sc.div, st);
-    const unsigned gN = (unsigned)((N + 127) / 128);
-    count_launch();
-    fhmm_node_pass_a<<<gN, 128, 0, st>>>(S, L, Le, N, logE, aux, X1, X2);
-    rc = cy2p_propagate_rows(plan, X1, Y1, S + L, 0, N, stream);
-    if (rc) return rc;
-    count_launch();
-    csr_times_small<<<(unsigned)(((int64_t)N * L + 255) / 256), 256, 0, st>>>(N, L, plan->d_indptr, plan->d_indices,
-                                                                             plan->d_data, X2, TP);
-    count_launch();
-    fhmm_node_pass_b<<<gN, 128, 0, st>>>(S, L, Le, N, logE, aux, X1, X2, Y1, scal, K);
-    count_launch();
-    fhmm_node_pass_c<<<gN, 128, 0, st>>>(S, L, Le, N, K, w.f.nsplit, logE, aux, X1, X2, Y1, TP,
-                                         (const float *)(ws + w.f.split), scal, w_excl, w_orth, w_tpm, d_gE);
-    count_launch();
-    fhmm_emission_grad_finish<<<(unsigned)(((int64_t)K * N + 255) / 256), 256, 0, st>>>(N, K, logE, scal + sc.rowsum,
-                                                                                       d_gE);
-    count_launch();
-    fhmm_ll_nodes<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(S, L, Le, N, I, logE, (const double *)(ws + w.f.row_lse),
-                                                               (double *)(ws + w.f.llv));
-    const int nparts = (N + 255) / 256;
-    count_launch();
-    lse_partials<<<nparts, 256, 0, st>>>(N, (const double *)(ws + w.f.llv), (double2 *)(ws + w.f.llpart));
-    count_launch();
-    lse_combine<<<1, 256, 0, st>>>(nparts, (const double2 *)(ws + w.f.llpart), scal + sc.ll);
-    // fold the lineage axis, then the single-chain backward (FHMM kernels with L = 1)
-    count_launch();
-    lssm_glue_backward<<<S, 256, 0, st>>>(S, L, I, restricted, K, (const float *)(ws + w.lsmall),
-                                          (const double *)(ws + w.f.Hlin), (const float *)(ws + w.f.gG), scal, aux,
-                                          w_sparse, w_excl, w_orth, w_tpm, (float *)(ws + w.gG1), scal1, d_gw, d_terms);
-    const int NB = (I + w.P1 - 1) / w.P1;
-    CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_local1));
-    count_launch();
-    fhmm_bwd_local<<<NB, 32, w.smem_local1, st>>>(S, 1, I, w.P1, 1, S, (const float *)(ws + w.small1),
-                                                  (const float *)(ws + w.aux1), (const float *)(ws + w.gG1), scal1,
-                                                  (float *)(ws + w.f.gH));
-    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bwd1));
-    float *tmp = (float *)(ws + w.tmp);
-    count_launch();
-    fhmm_small_backward<<<1, 512, w.smem_bwd1, st>>>(S, 1, I, w.P1, 1, S, (const float *)(ws + w.small1),
-                                                     (const double *)(ws + w.f.Hlin), (const double *)(ws + w.Apow1),
-                                                     (const float *)(ws + w.aux1), (const float *)(ws + w.gG1), scal1,
-                                                     w_sparse, 0.f, 0.f, 0.f, (float *)(ws + w.f.gH), d_gpi, tmp,
-                                                     d_gA, tmp + 4);
-    CY2P_CUDA(cudaGetLastError());
-    return CY2P_OK;
+    return lssm_loss_core(plan, S, L, Le, N, I, restricted, w, ws, d_D, h_weights, d_terms, d_gpi, d_gw, d_gE, d_gA, 0,
+                          stream);
 }
 
 int32_t cy2p_lssm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted, const float *theta_pi,
@@ -1936,6 +2105,126 @@ int32_t cy2p_lssm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t res
     float *small_exp = (float *)(ws + w.f.small), *Bexp = (float *)(ws + w.f.gH);  // both free on this path
     count_launch();
     lssm_expand_decode<<<64, 256, 0, st>>>(S, L, Le, I, (const float *)(ws + w.lsmall), bm, small_exp, Bexp);
+    const size_t smem = sizeof(float) * ((size_t)L * S * S + 2 * (size_t)S * L + 2 * L);
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_decode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    count_launch();
+    fhmm_decode_small<<<1, 512, smem, st>>>(S, L, L, I, small_exp, Bexp, d_log_alpha, d_log_probs, d_log_beta,
+                                            d_log_gamma, d_log_delta, d_psi, d_log_max, d_best_path);
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ NSSM
+size_t cy2p_nssm_ws_bytes(int32_t S, int32_t L, int32_t N, int32_t I) {
+    if (S < 1 || L < 1 || N < 1 || I < 1 || S > kMaxS || L > kMaxL || S * L > kMaxK) return 0;
+    return nssm_layout(S, L, S, N, I).total;
+}
+
+int32_t cy2p_nssm_forward(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted, const float *theta_pi,
+                          const float *theta_cw, const float *theta_E, const float *theta_A, float *d_pred,
+                          float *d_hidden, float *d_joint, float *d_logE, float *d_logcw, float *d_small, void *d_ws,
+                          size_t ws_bytes, void *stream) {
+    const int Sc = restricted ? 1 : S, K = S * L;
+    const NssmWs w = nssm_layout(S > 0 ? S : 1, L > 0 ? L : 1, Sc > 0 ? Sc : 1, N > 0 ? N : 1, I > 0 ? I : 1);
+    int32_t rc = nssm_check(S, L, N, I, w, d_ws, ws_bytes);
+    if (rc) return rc;
+    CY2P_REQUIRE(theta_pi && theta_cw && theta_E && theta_A, "null parameter");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    rc = nssm_run_forward(S, L, Sc, N, I, theta_pi, theta_cw, theta_E, theta_A, w, ws, st);
+    if (rc) return rc;
+    const float *logEhat = (const float *)(ws + w.l.f.logE);
+    if (d_pred) {
+        CY2P_CUDA(cudaMemsetAsync(ws + w.l.f.gG, 0, sizeof(float) * (size_t)I * K, st));
+        CY2P_CUDA(cudaMemsetAsync(ws + w.l.f.scal, 0, sizeof(double) * ScalarOffsets(S, L, K).total, st));
+        dispatch_data_pass(N, I, K, w.l.f, logEhat, (const float *)(ws + w.l.f.G), nullptr, d_pred,
+                           (float *)(ws + w.l.f.split), (float *)(ws + w.l.f.gG), (double *)(ws + w.l.f.scal), st);
+    }
+    if (d_hidden)
+        CY2P_CUDA(cudaMemcpyAsync(d_hidden, ws + w.l.f.hidden, sizeof(float) * (size_t)I * S, cudaMemcpyDeviceToDevice, st));
+    if (d_logE)
+        CY2P_CUDA(cudaMemcpyAsync(d_logE, ws + w.logE0, sizeof(float) * (size_t)S * N, cudaMemcpyDeviceToDevice, st));
+    if (d_logcw)
+        CY2P_CUDA(cudaMemcpyAsync(d_logcw, ws + w.logcw, sizeof(float) * (size_t)Sc * N * L, cudaMemcpyDeviceToDevice, st));
+    if (d_small)
+        CY2P_CUDA(cudaMemcpyAsync(d_small, ws + w.l.lsmall, sizeof(float) * LssmSmallOffsets(S, L).total,
+                                  cudaMemcpyDeviceToDevice, st));
+    if (d_joint) {
+        dim3 grid((unsigned)((N + 255) / 256), (unsigned)(I * S * L));
+        count_launch();
+        lssm_joint_kernel<<<grid, 256, 0, st>>>(S, L, L, N, I, logEhat, (const float *)(ws + w.l.f.hidden),
+                                                (const float *)(ws + w.l.lsmall) + LssmSmallOffsets(S, L).log_w,
+                                                d_joint);
+    }
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+int32_t cy2p_nssm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted,
+                            const float *theta_pi, const float *theta_cw, const float *theta_E, const float *theta_A,
+                            const float *d_D, const float *h_weights, float *d_terms, float *d_gpi, float *d_gcw,
+                            float *d_gE, float *d_gA, void *d_ws, size_t ws_bytes, void *stream) {
+    const int Sc = restricted ? 1 : S, K = S * L;
+    const NssmWs w = nssm_layout(S > 0 ? S : 1, L > 0 ? L : 1, Sc > 0 ? Sc : 1, N > 0 ? N : 1, I > 0 ? I : 1);
+    int32_t rc = nssm_check(S, L, N, I, w, d_ws, ws_bytes);
+    if (rc) return rc;
+    CY2P_REQUIRE(plan && theta_pi && theta_cw && theta_E && theta_A && d_D && h_weights, "null pointer");
+    CY2P_REQUIRE(d_terms && d_gpi && d_gcw && d_gE && d_gA, "null output");
+    CY2P_REQUIRE(plan->n == N, "plan size != num_nodes");
+    cudaStream_t st = (cudaStream_t)stream;
+    CY2P_CUDA(cudaSetDevice(plan->device));
+    char *ws = (char *)d_ws;
+    const ScalarOffsets sc(S, L, K);
+    CY2P_CUDA(cudaMemsetAsync(ws + w.l.f.gG, 0, sizeof(float) * (size_t)I * K, st));
+    CY2P_CUDA(cudaMemsetAsync(ws + w.l.f.scal, 0, sizeof(double) * sc.total, st));
+    CY2P_CUDA(cudaMemsetAsync(ws + w.l.scal1, 0, sizeof(double) * ScalarOffsets(S, 1, S).total, st));
+    rc = nssm_run_forward(S, L, Sc, N, I, theta_pi, theta_cw, theta_E, theta_A, w, ws, st);
+    if (rc) return rc;
+    rc = lssm_loss_core(plan, S, L, L, N, I, 0, w.l, ws, d_D, h_weights, d_terms, d_gpi, (float *)(ws + w.glw),
+                        (float *)(ws + w.gEt), d_gA, 1, stream);
+    if (rc) return rc;
+    double *rowsum0 = (double *)(ws + w.rowsum0) + S;
+    count_launch();
+    nssm_backward_nodes<<<(N + 127) / 128, 128, 0, st>>>(S, L, Sc, N, (const float *)(ws + w.gEt),
+                                                         (const float *)(ws + w.l.f.logE), (const float *)(ws + w.glw),
+                                                         (const double *)(ws + w.l.f.scal) + sc.rowsum,
+                                                         (const float *)(ws + w.logcw), d_gE, rowsum0, d_gcw);
+    count_launch();
+    fhmm_emission_grad_finish<<<(unsigned)(((int64_t)S * N + 255) / 256), 256, 0, st>>>(
+        N, S, (const float *)(ws + w.logE0), rowsum0, d_gE);
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+int32_t cy2p_nssm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted, const float *theta_pi,
+                         const float *theta_cw, const float *theta_E, const float *theta_A, const float *d_D,
+                         float *d_log_alpha, float *d_log_probs, float *d_log_beta, float *d_log_gamma,
+                         float *d_log_delta, float *d_psi, float *d_log_max, float *d_best_path, void *d_ws,
+                         size_t ws_bytes, void *stream) {
+    const int Sc = restricted ? 1 : S, K = S * L;
+    const NssmWs w = nssm_layout(S > 0 ? S : 1, L > 0 ? L : 1, Sc > 0 ? Sc : 1, N > 0 ? N : 1, I > 0 ? I : 1);
+    int32_t rc = nssm_check(S, L, N, I, w, d_ws, ws_bytes);
+    if (rc) return rc;
+    CY2P_REQUIRE(theta_pi && theta_cw && theta_E && theta_A && d_D, "null input");
+    CY2P_REQUIRE(d_log_alpha && d_log_probs && d_log_beta && d_log_gamma && d_log_delta && d_psi && d_log_max &&
+                     d_best_path, "null output");
+    CY2P_REQUIRE(S * L <= 512, "decoders need S*L <= 512");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)d_ws;
+    rc = nssm_run_forward(S, L, Sc, N, I, theta_pi, theta_cw, theta_E, theta_A, w, ws, st);
+    if (rc) return rc;
+    // Bmat over the normalised rows; log r joins it in lssm_expand_decode (log_weights = log Ehat + log r, _NSSM.py:80)
+    const float *logEhat = (const float *)(ws + w.l.f.logE);
+    float *rowmax = (float *)(ws + w.l.f.gG);
+    float *bm = (float *)(ws + w.l.f.X1);
+    if ((size_t)I * K > (size_t)N * (S + L)) bm = (float *)(ws + w.l.f.split);
+    count_launch();
+    fhmm_row_max<<<K, 256, 0, st>>>(N, logEhat, rowmax);
+    count_launch();
+    fhmm_bmat<<<dim3(I, K), 256, 0, st>>>(N, K, d_D, logEhat, rowmax, bm);
+    float *small_exp = (float *)(ws + w.l.f.small), *Bexp = (float *)(ws + w.l.f.gH);
+    count_launch();
+    lssm_expand_decode<<<64, 256, 0, st>>>(S, L, L, I, (const float *)(ws + w.l.lsmall), bm, small_exp, Bexp);
     const size_t smem = sizeof(float) * ((size_t)L * S * S + 2 * (size_t)S * L + 2 * L);
     CY2P_CUDA(cudaFuncSetAttribute(fhmm_decode_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     count_launch();

@@ -210,6 +210,31 @@ int32_t cy2p_lssm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t res
                          float *d_log_delta, float *d_psi, float *d_log_max, float *d_best_path, void *d_ws,
                          size_t ws_bytes, void *stream);
 
+/* ---- K3c: latent state-space model with node-level lineage weights (NSSM) -----------------------
+ * Replaces NSSM.forward_model (_NSSM.py:76-118), one epoch of trainer.train on an NSSM and
+ * NSSM.filtering / smoothing / viterbi (_NSSM.py:120-249). Parameter shapes:
+ *   theta_pi [S], theta_cw [Sc][N][L] (Sc = 1 if restricted else S), theta_E [S][N], theta_A [S][S]
+ *   d_hidden [I][S]; d_joint [I][S][L][N] (the layout forward_model returns after its permute, _NSSM.py:111);
+ *   d_logE [S][N] and d_logcw [Sc][N][L]: the two log-softmaxes; d_small: the LSSM layout with
+ *   log_w = log r[s][l], r[s][l] = sum_n E[s][n] cw[s'][n][l] (cy2p_lssm_small_floats(S,L) floats)
+ *   gradients d_gpi [S], d_gcw [Sc][N][L], d_gE [S][N], d_gA [S][S];  requires S*L <= 64. */
+size_t cy2p_nssm_ws_bytes(int32_t S, int32_t L, int32_t N, int32_t I);
+int32_t cy2p_nssm_forward(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted,
+                          const float *theta_pi, const float *theta_cw, const float *theta_E,
+                          const float *theta_A, float *d_pred, float *d_hidden, float *d_joint,
+                          float *d_logE, float *d_logcw, float *d_small, void *d_ws, size_t ws_bytes,
+                          void *stream);
+int32_t cy2p_nssm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted,
+                            const float *theta_pi, const float *theta_cw, const float *theta_E,
+                            const float *theta_A, const float *d_D, const float *h_weights,
+                            float *d_terms, float *d_gpi, float *d_gcw, float *d_gE, float *d_gA,
+                            void *d_ws, size_t ws_bytes, void *stream);
+int32_t cy2p_nssm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t restricted, const float *theta_pi,
+                         const float *theta_cw, const float *theta_E, const float *theta_A, const float *d_D,
+                         float *d_log_alpha, float *d_log_probs, float *d_log_beta, float *d_log_gamma,
+                         float *d_log_delta, float *d_psi, float *d_log_max, float *d_best_path, void *d_ws,
+                         size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,27 @@ def lssm_forward_model(theta_pi, theta_w, theta_E, theta_A, num_iters, want_join
     return pred, (joint if want_joint else None), hidden, log_A
 
 
+def nssm_forward_model(theta_pi, theta_w, theta_E, theta_A, num_iters, want_joint=True):
+    """reference: cy2path/models/_NSSM.py:76-118 (NSSM: one latent chain, node-level chain weights).
+
+    theta_pi [S], theta_w [1|S,N,L], theta_E [S,N], theta_A [S,S].
+    log_weights[s,n,l] = log E[s,n] + log cw[s',n,l]                                     (:80-82)
+    joint[t,s,n,l] = log_weights[s,n,l] + hidden[t,s], returned permuted to [I,S,L,N]    (:97-112)
+    Returns pred [I,N], joint [I,S,L,N] (or None), hidden [I,S], log A [S,S]."""
+    log_pi = torch.log_softmax(theta_pi, dim=0)
+    log_cw = torch.log_softmax(theta_w, dim=-1)
+    log_E = torch.log_softmax(theta_E, dim=-1)
+    log_A = torch.log_softmax(theta_A, dim=-1)
+    log_weights = log_E.unsqueeze(-1) + log_cw  # [S, N, L]
+    h = [log_pi]
+    for _ in range(1, num_iters):
+        h.append(LSE(h[-1].unsqueeze(-1) + log_A, dim=0))
+    hidden = torch.stack(h, 0)
+    joint = log_weights.unsqueeze(0) + hidden[:, :, None, None]  # [I, S, N, L]
+    pred = LSE(LSE(joint, dim=1), dim=-1)
+    return pred, (joint.permute(0, 1, 3, 2) if want_joint else None), hidden, log_A
+
+
 def log_domain_mean(x, dim=0):
     """reference: cy2path/utils.py:139-145."""
     return LSE(x, dim) - math.log(x.shape[dim])
@@ -91,6 +112,9 @@ def loss_terms(theta_pi, theta_w, theta_E, theta_A, D, TPM, weights=(1.0, 0.1, 0
     if model == "lssm":  # the trainer is shared between the model classes (trainer.py:134-196)
         S, L = theta_w.shape
         pred, joint, hidden, log_A_mix = lssm_forward_model(theta_pi, theta_w, theta_E, theta_A, I)
+    elif model == "nssm":
+        S, L = theta_E.shape[0], theta_w.shape[-1]
+        pred, joint, hidden, log_A_mix = nssm_forward_model(theta_pi, theta_w, theta_E, theta_A, I)
     else:
         S, L = theta_pi.shape
         pred, joint, hidden, log_A_mix = forward_model(theta_pi, theta_w, theta_E, theta_A, I)

@@ -94,7 +94,8 @@ def golden_fhmm(ref, name, S, L, N, I, restricted, seed, k=6, model_cls="FHMM"):
         ref.methods.compute_log_likelihood(model)
         ll = model.log_likelihood.item()
     # one epoch with a zero-learning-rate optimiser: parameters stay put, .grad survives
-    model.train(D, TPM=TPM, num_epochs=1, TPM_weight=0.05,
+    model.train(D, TPM=TPM, num_epochs=1, sparsity_weight=1.0, exclusivity_weight=0.1, orthogonality_weight=0.1,
+                TPM_weight=0.05,  # explicit: NSSM.train defaults to exclusivity_weight=1e-5 (_NSSM.py:259)
                 optimizer=torch.optim.SGD(model.parameters(), lr=0.0))
     grads = {"grad_" + k_: p.grad.detach().clone().numpy() for k_, p in model.named_parameters()}
     terms = dict(loss=model.loss_values[0], divergence=model.divergence_values[0],
@@ -140,6 +141,9 @@ def main():
         (golden_fhmm, "lssm_restricted.npz", dict(S=4, L=3, N=60, I=25, restricted=True, seed=31, model_cls="LSSM")),
         (golden_fhmm, "lssm_unrestricted.npz", dict(S=3, L=2, N=50, I=20, restricted=False, seed=32, model_cls="LSSM")),
         (golden_fhmm, "lssm_single_chain.npz", dict(S=5, L=1, N=40, I=15, restricted=True, seed=33, model_cls="LSSM")),
+        (golden_fhmm, "nssm_restricted.npz", dict(S=4, L=3, N=60, I=25, restricted=True, seed=41, model_cls="NSSM")),
+        (golden_fhmm, "nssm_unrestricted.npz", dict(S=3, L=2, N=50, I=20, restricted=False, seed=42, model_cls="NSSM")),
+        (golden_fhmm, "nssm_single_chain.npz", dict(S=5, L=1, N=40, I=15, restricted=True, seed=43, model_cls="NSSM")),
     ]
     for fn, name, kw in jobs:
         if len(sys.argv) > 1 and not any(name.startswith(p) for p in sys.argv[1:]):

@@ -17,13 +17,14 @@ NAMES = ("unnormalized_state_init", "unnormalized_chain_weights", "unnormalized_
 
 
 GOLDEN = ["fhmm_restricted.npz", "fhmm_unrestricted.npz", "fhmm_single_chain.npz",
-          "lssm_restricted.npz", "lssm_unrestricted.npz", "lssm_single_chain.npz"]  # LSSM: SURVEY §8 f-3
+          "lssm_restricted.npz", "lssm_unrestricted.npz", "lssm_single_chain.npz",  # LSSM / NSSM: SURVEY §8 f-3
+          "nssm_restricted.npz", "nssm_unrestricted.npz", "nssm_single_chain.npz"]
 
 
 def _cls(name):
     from cy2path_b200 import models
 
-    return models.LSSM if name.startswith("lssm") else models.FHMM
+    return {"fhmm": models.FHMM, "lssm": models.LSSM, "nssm": models.NSSM}[name[:4]]
 
 
 def _model_from(g, name="fhmm"):
@@ -72,7 +73,7 @@ def test_loss_terms_and_gradients_match_reference_golden(golden, name):
         assert np.abs(gq.cpu().numpy() - rg).max() <= 1e-5 + 1e-3 * np.abs(rg).max(), nme
 
 
-@pytest.mark.parametrize("kind", ["fhmm", "lssm"])
+@pytest.mark.parametrize("kind", ["fhmm", "lssm", "nssm"])
 @pytest.mark.parametrize("S,L,restricted,N,I", [(10, 4, True, 2000, 60), (5, 3, False, 1500, 40), (12, 2, True, 777, 33),
                                                  (3, 1, False, 300, 9)])
 def test_mid_size_vs_oracle_autograd(S, L, restricted, N, I, kind):
@@ -114,7 +115,7 @@ def test_mid_size_vs_oracle_autograd(S, L, restricted, N, I, kind):
     assert np.abs(pred.cpu().numpy() - ref["pred"].detach().numpy()).max() <= 2e-5
 
 
-@pytest.mark.parametrize("name", ["fhmm_restricted.npz", "lssm_restricted.npz"])
+@pytest.mark.parametrize("name", ["fhmm_restricted.npz", "lssm_restricted.npz", "nssm_restricted.npz"])
 def test_trainer_drop_in(golden, name):
     g = golden(name)
     m = _model_from(g, name)

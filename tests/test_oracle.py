@@ -75,9 +75,10 @@ def _params(g):
 
 
 @pytest.mark.parametrize("name", ["fhmm_restricted.npz", "fhmm_unrestricted.npz", "fhmm_single_chain.npz",
-                                  "lssm_restricted.npz", "lssm_unrestricted.npz", "lssm_single_chain.npz"])
+                                  "lssm_restricted.npz", "lssm_unrestricted.npz", "lssm_single_chain.npz",
+                                  "nssm_restricted.npz", "nssm_unrestricted.npz", "nssm_single_chain.npz"])
 def test_fhmm_oracle_matches_reference(golden, name):
-    """FHMM and LSSM (the same trainer drives both, reference trainer.py:134-196)."""
+    """FHMM, LSSM and NSSM (the same trainer drives both, reference trainer.py:134-196)."""
     g = golden(name)
     kind = name.split("_")[0]
     th = [t.requires_grad_(True) for t in _params(g)]
