@@ -125,6 +125,40 @@ def golden_fhmm(ref, name, S, L, N, I, restricted, seed, k=6, model_cls="FHMM"):
     print(name, "loss", terms["loss"], "ll", ll)
 
 
+def golden_dynamics(ref, name, mode, S, L, N, I, restricted, seed, k=6):
+    """infer_dynamics + latent_state_selection of the reference on a seeded model, one zero-learning-rate epoch
+    (the parameters stay at their initial values, so the stored outputs are functions of params0 only)."""
+    import importlib
+
+    dyn = importlib.import_module("cy2path.dynamics.infer_dynamics")
+    post = importlib.import_module("cy2path.dynamics.infer_posthoc")
+    g = knn_velocity_tpm(N, k=k, seed=seed)
+    ad = adata_for(g, ref)
+    init_p, _ = ref.utils.check_root_init(ad, init="root_cells")
+    stat = g["end_points"] / g["end_points"].sum()
+    _, shm, _ = ref.sampling.iterate_state_probability(ad, init=init_p, stationary=stat, max_iter=I)
+    ad.uns["state_probability_sampling"] = {"state_history": shm}
+    torch.manual_seed(seed)
+    model = getattr(ref.models, mode)(S, L, N, I, restricted=restricted, use_gpu=False)
+    params0 = {k_: v.detach().clone().numpy() for k_, v in model.state_dict().items()}
+    dyn.infer_dynamics(ad, model=model, num_epochs=1, mode=mode, save_model=None,
+                       optimizer=torch.optim.SGD(model.parameters(), lr=0.0))
+    ld = ad.uns["latent_dynamics"]
+    out = {}
+    for grp in ("model_outputs", "model_params", "conditional_probabilities"):
+        for key, val in ld[grp].items():
+            out[grp + "/" + key] = np.asarray(val)
+    post.latent_state_selection(ad, criteria="argmax_joint", min_ratio=None)
+    for key, val in ld["conditional_probabilities"].items():
+        if key.endswith("_selected"):
+            out["conditional_probabilities/" + key] = np.asarray(val)
+    out["selected_states"] = np.asarray(ld["posthoc_computations"]["selected_states"])
+    np.savez_compressed(os.path.join(HERE, name), **csr_fields(g["T"]), D=shm, S=S, L=L, N=N, I=I,
+                        restricted=restricted, mode=mode, root_cells=g["root_cells"], end_points=g["end_points"],
+                        log_likelihood=np.float64(ld["log_likelihood"]), **params0, **out)
+    print(name, sorted(out)[:3], "...", len(out), "arrays")
+
+
 def main():
     """``python make_golden.py [prefix ...]`` regenerates every fixture, or those whose file name starts with a prefix."""
     import sys
@@ -144,6 +178,9 @@ def main():
         (golden_fhmm, "nssm_restricted.npz", dict(S=4, L=3, N=60, I=25, restricted=True, seed=41, model_cls="NSSM")),
         (golden_fhmm, "nssm_unrestricted.npz", dict(S=3, L=2, N=50, I=20, restricted=False, seed=42, model_cls="NSSM")),
         (golden_fhmm, "nssm_single_chain.npz", dict(S=5, L=1, N=40, I=15, restricted=True, seed=43, model_cls="NSSM")),
+        (golden_dynamics, "dynamics_fhmm.npz", dict(mode="FHMM", S=4, L=3, N=60, I=25, restricted=True, seed=51)),
+        (golden_dynamics, "dynamics_lssm.npz", dict(mode="LSSM", S=3, L=2, N=50, I=20, restricted=False, seed=52)),
+        (golden_dynamics, "dynamics_nssm.npz", dict(mode="NSSM", S=4, L=2, N=40, I=15, restricted=True, seed=53)),
     ]
     for fn, name, kw in jobs:
         if len(sys.argv) > 1 and not any(name.startswith(p) for p in sys.argv[1:]):
