@@ -161,6 +161,23 @@ def to_host(t):
     return out.numpy()
 
 
+def to_host_many(tensors):
+    """to_host for several device tensors with one stream synchronisation (None entries pass through)."""
+    torch = _torch()
+    outs, dev = [], None
+    for t in tensors:
+        if t is None:
+            outs.append(None)
+            continue
+        dev = t.device
+        o = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        o.copy_(t, non_blocking=True)
+        outs.append(o)
+    if dev is not None:
+        torch.cuda.current_stream(dev).synchronize()
+    return [None if o is None else o.numpy() for o in outs]
+
+
 class Plan:
     """Device-resident T and T^T for one transition matrix on one device (cy2p_plan)."""
 

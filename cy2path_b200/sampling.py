@@ -73,6 +73,20 @@ def batch_convergence(eps, tol, max_iter):
     return np.where(conv < max_iter, conv, max_iter).astype(np.int64)
 
 
+def batch_convergence_device(eps, tol, max_iter):
+    """batch_convergence on the device tensor eps [iters, B] (float64): same comparisons, so the same integers;
+    saves a host pass over iters x B values per call."""
+    import torch
+
+    if eps.shape[0] < 2:
+        return torch.full((eps.shape[1],), max_iter, dtype=torch.int64, device=eps.device)
+    above = (eps[1:] - eps[:-1]).abs() > tol  # [iters-1, B]
+    idx = torch.arange(above.shape[0], device=eps.device, dtype=torch.int64)[:, None]
+    last = torch.where(above, idx, torch.full_like(idx, -1)).amax(0)
+    conv = torch.where(last >= 0, last + 2, torch.full_like(last, max_iter))
+    return torch.clamp(conv, max=max_iter)
+
+
 def iterate_state_probability(adata, matrix_key="T_forward", init=None, stationary=None, max_iter=1000, tol=1e-5):
     """reference sampling.py:29-60. Returns (state_history, state_history_max_iter, convergence_check);
     histories are float64 host arrays as in the reference. The single-start case runs with a float64
@@ -124,11 +138,11 @@ def propagate_batch(adata_or_T, X0, iters, stationary=None, matrix_key="T_forwar
     x0 = _lib.to_device(X0, tdt, plan.device)
     out = _lib.propagate(plan, x0, int(iters), stationary=stationary, want_final=True, history_stride=0,
                          want_eps=stationary is not None)
-    res = {"final": out["final"] if return_device else _lib.to_host(out["final"])}
-    if out["eps"] is not None:
-        eps = _lib.to_host(out["eps"])
+    conv_d = batch_convergence_device(out["eps"], tol, int(iters)) if out["eps"] is not None else None
+    fin, eps, conv = _lib.to_host_many([None if return_device else out["final"], out["eps"], conv_d])
+    res = {"final": out["final"] if return_device else fin}
+    if eps is not None:
         res["eps"] = eps
-        conv = batch_convergence(eps, tol, iters)
         res["convergence"] = conv
     return res
 

@@ -66,9 +66,42 @@ def eigs(T, k=10, eps=1e-3):
         return np.empty(0), np.zeros((T.shape[0], 0))
 
 
-def estimate_stationary_state(adata, matrix_key="T_forward"):
-    """reference utils.py:104-118: the single leading left eigenvector, else the end_points prior."""
-    vecs = eigs(adata.obsp[matrix_key])[1]
+def eigs_device(T, k=10, eps=1e-3, tol=1e-7, max_updates=20000):
+    """``eigs`` answered on the device: block subspace iteration whose update is the K1 kernel with B = k columns
+    in float64 (cy2path_b200/stationary.py). Returns (values, |vectors|) like ``eigs``."""
+    import torch
+
+    from .dist import cuda_row_update
+    from .sampling import get_plan
+    from .stationary import dominant_left_eigenpairs
+
+    plan = get_plan(T)
+    update = cuda_row_update(plan)
+
+    def apply_T(X):
+        X = X.contiguous()
+        Y = torch.empty_like(X)
+        update(X, Y, 0, plan.n)
+        return Y
+
+    vals, vecs, info = dominant_left_eigenpairs(apply_T, plan.n, k=k, eps=eps, tol=tol, max_updates=max_updates,
+                                                device=plan.device)
+    if not info["converged"]:
+        logger.warning("subspace iteration stopped at %d updates with residual %.2e", info["updates"], info["residual"])
+    return vals, vecs
+
+
+def estimate_stationary_state(adata, matrix_key="T_forward", method=None):
+    """reference utils.py:104-118: the single leading left eigenvector, else the end_points prior.
+
+    ``method``: "arpack" (host scipy, the default: closest to the scvelo call the reference makes) or "device"
+    (``eigs_device``); the environment variable CY2P_STATIONARY sets the default."""
+    import os
+
+    method = method or os.environ.get("CY2P_STATIONARY", "arpack")
+    if method not in ("arpack", "device"):
+        raise ValueError("method must be 'arpack' or 'device'")
+    vecs = (eigs_device if method == "device" else eigs)(adata.obsp[matrix_key])[1]
     if vecs.shape[1] == 1:
         stat = vecs / vecs.sum()
     else:

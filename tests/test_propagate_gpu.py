@@ -333,3 +333,25 @@ def test_edge_cases_tiny_graphs_empty_rows_and_short_runs():
     T64.indptr = T64.indptr.astype(np.int64)
     _, h64, _ = c2p.iterate_state_probability(Duck(T64), init=init, stationary=stat, max_iter=12)
     assert np.abs(h64 - ref).max() <= 1e-14
+
+
+def test_batched_convergence_cut_matches_reference_rule(golden):
+    """propagate_batch's per-start convergence (computed on the device) against the reference's rule applied
+    to each column of the returned eps history (sampling.py:13-25, 48-57), and against the oracle's eps."""
+    from cy2path_b200.sampling import check_convergence_criteria, propagate_batch
+
+    g = golden("msm_small.npz")
+    T, n = g["T"], g["T"].shape[0]
+    rng = np.random.default_rng(8)
+    B, iters, tol = 12, 120, float(g["tol"])
+    X0 = np.zeros((n, B), dtype=np.float32)
+    X0[:, 0] = (g["init"] / g["init"].sum()).astype(np.float32)
+    for b in range(1, B):
+        X0[rng.choice(n, 5, replace=False), b] = 0.2
+    r = propagate_batch(T, X0, iters, stationary=g["stationary"], tol=tol, precision="fp64")
+    assert r["eps"].shape == (iters, B) and r["convergence"].shape == (B,) and r["convergence"].dtype == np.int64
+    for b in range(B):
+        c = check_convergence_criteria(r["eps"][:, b], tol)
+        assert r["convergence"][b] == (c if (c is not None and c < iters) else iters)
+    assert r["convergence"][0] == int(g["convergence"])  # column 0 is the golden run's start
+    assert (r["convergence"] < iters).any()
