@@ -65,6 +65,15 @@ struct cy2p_plan {
     cy2p::Pair *d_r_pairs_pp = nullptr;    // sources as permuted positions  (permuted iterate -> permuted iterate)
     cy2p::Pair *d_r_pairs_op = nullptr;    // sources as original ids        (original iterate -> permuted iterate)
     double span_identity = 0.0, span_reordered = 0.0;  // mean |pos(i) - pos(j)| over the stored entries
+    // Staged gather (propagate.cu spmm_staged): the permuted rows cut into blocks whose distinct sources fit a CTA's
+    // shared memory; sources are named by their index in the block's list
+    int32_t nblk = 0;                      // 0 = not built
+    int32_t blk_ucap = 0;                  // max distinct sources of a block
+    int32_t *d_blk_row = nullptr;          // [nblk+1] first permuted row of each block
+    int32_t *d_blk_uptr = nullptr;         // [nblk+1] offsets into d_blk_usrc
+    int32_t *d_blk_usrc = nullptr;         // distinct sources (permuted positions, ascending) of each block
+    cy2p::Pair *d_r_pairs_lp = nullptr;    // d_r_pairs_pp with src replaced by the index in the block's list
+    double blk_reuse = 0.0;                // stored entries / distinct sources, averaged over the blocks
 };
 
 namespace cy2p {

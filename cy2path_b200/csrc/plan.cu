@@ -168,6 +168,10 @@ static void plan_free(cy2p_plan *p) {
     cudaFree(p->d_r_indptr);
     cudaFree(p->d_r_pairs_pp);
     cudaFree(p->d_r_pairs_op);
+    cudaFree(p->d_blk_row);
+    cudaFree(p->d_blk_uptr);
+    cudaFree(p->d_blk_usrc);
+    cudaFree(p->d_r_pairs_lp);
     delete p;
 }
 

@@ -49,6 +49,18 @@ struct Vec<float, 4> {
     }
 };
 template <>
+struct Vec<float, 2> {
+    using V = float2;
+    static __device__ __forceinline__ V zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ V load(const float *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
+    static __device__ __forceinline__ void store(float *p, V v) { *reinterpret_cast<float2 *>(p) = v; }
+    static __device__ __forceinline__ void fma(V &a, float t, V x) {
+        a.x = fmaf(t, x.x, a.x);
+        a.y = fmaf(t, x.y, a.y);
+    }
+    static __device__ __forceinline__ double get(const V &v, int k) { return (double)(k == 0 ? v.x : v.y); }
+};
+template <>
 struct Vec<float, 1> {
     using V = float;
     static __device__ __forceinline__ V zero() { return 0.f; }
@@ -234,6 +246,143 @@ spmm_gather_sm(int32_t n_rows, int32_t rows_per_cta, int32_t nslabs, int32_t num
             const int32_t slab = q / cnt, rg = rg0 + q % cnt;
             const int32_t row0 = rg * rows_per_cta;
             gather_block<T, VEC, EPS>(a, row0, min(row0 + rows_per_cta, n_rows), slab, rg % kEpsCopies);
+        }
+    }
+}
+
+// Staged gather for the permuted -> permuted updates (the bulk of a long batched run). The plan cuts the permuted
+// rows into blocks whose distinct sources fit shared memory (reorder.cu). A CTA takes one block and walks a run of
+// 256-byte column slabs with a two-stage pipeline: while the rows of slab s are formed out of one shared-memory
+// buffer, cp.async copies every distinct source segment of slab s+1 from L2 into the other buffer (all copies
+// independent, no registers held). A source that several rows of the block share costs one L2 -> SM transfer instead
+// of one per row — the L2 -> SM fill path is what bounds spmm_gather (profiles/README_r01.md §2) — and the block's
+// (index, value) pairs and row pointers are read once per run of slabs instead of once per slab.
+constexpr int kSegBytes = 256;    // bytes of one staged source segment = 32 lanes x VEC x sizeof(T)
+constexpr int kStagedWarps = 16;  // warps per CTA of the staged kernel
+constexpr int kStagedMaxRows = 64, kStagedMaxPairs = 2048;
+
+template <typename T>
+struct StagedArgs {
+    const int32_t *blk_row, *blk_uptr, *blk_usrc;
+    const int32_t *r_indptr;
+    const Pair *lpairs;
+    const int32_t *dest_ids;
+    const T *Xin;
+    T *Xout;
+    uint32_t ld;  // both iterates are scratch tiles with the same pitch
+    int32_t ncols, nslabs, slabs_per_cta, ucap;
+    const double *stationary;
+    double *eps_acc;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+template <typename T, int VEC, bool EPS>
+__global__ void __launch_bounds__(kStagedWarps * 32, 1) spmm_staged(StagedArgs<T> a) {
+    static_assert(32 * VEC * sizeof(T) == kSegBytes, "one warp spans one staged segment");
+    using VT = Vec<T, VEC>;
+    using V = typename VT::V;
+    constexpr int kSegElems = kSegBytes / sizeof(T);
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    // layout: buf[2][ucap][kSegBytes] | pairs[kStagedMaxPairs] | rowptr[kStagedMaxRows + 1] | red
+    unsigned char *s_buf = s_dyn;
+    Pair *s_pairs = reinterpret_cast<Pair *>(s_dyn + 2 * (size_t)a.ucap * kSegBytes);
+    int32_t *s_rp = reinterpret_cast<int32_t *>(s_pairs + kStagedMaxPairs);
+    T *s_red = reinterpret_cast<T *>(s_rp + kStagedMaxRows + 4);  // [2][VEC][kStagedWarps][32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
+    const int32_t u0 = __ldg(a.blk_uptr + b), U = __ldg(a.blk_uptr + b + 1) - u0;
+    const int32_t row0 = __ldg(a.blk_row + b), row1 = __ldg(a.blk_row + b + 1);
+    const int nrows = row1 - row0;
+    const int slab0 = blockIdx.y * a.slabs_per_cta, slab1 = min(a.nslabs, slab0 + a.slabs_per_cta);
+    const uint32_t ld = a.ld;
+    // ---- prologue: this block's pairs and row pointers into shared memory; this warp's run of source ids into registers
+    const int32_t p0 = __ldg(a.r_indptr + row0);
+    const int32_t np = __ldg(a.r_indptr + row1) - p0;
+    for (int i = threadIdx.x; i < np; i += kStagedWarps * 32) s_pairs[i] = a.lpairs[p0 + i];
+    for (int i = threadIdx.x; i <= nrows; i += kStagedWarps * 32) s_rp[i] = __ldg(a.r_indptr + row0 + i) - p0;
+    const int per_warp = (U + kStagedWarps - 1) / kStagedWarps;  // <= 32 (ucap <= 512)
+    const int w0 = min(U, warp * per_warp), cnt = min(U, w0 + per_warp) - w0;
+    const int32_t mine = lane < cnt ? __ldg(a.blk_usrc + u0 + w0 + lane) : 0;
+    const int hw = lane >> 4, hl = lane & 15;
+    const uint64_t pitch = (uint64_t)ld * sizeof(T);
+    auto issue = [&](int slab, int stage) {  // half a warp per segment, 16 bytes per lane
+        const unsigned char *xin = reinterpret_cast<const unsigned char *>(a.Xin + (size_t)slab * 32 * VEC) + hl * 16;
+        unsigned char *dst = s_buf + (size_t)stage * a.ucap * kSegBytes + (size_t)w0 * kSegBytes + hl * 16;
+#pragma unroll 4
+        for (int i = 0; i < cnt; i += 2) {
+            const int32_t src = __shfl_sync(0xffffffffu, mine, min(i + hw, cnt - 1));
+            if (i + hw < cnt) cp_async16(dst + (size_t)(i + hw) * kSegBytes, xin + (uint64_t)(uint32_t)src * pitch);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(slab0, 0);
+    for (int slab = slab0; slab < slab1; ++slab) {
+        const int stage = (slab - slab0) & 1;
+        if (slab + 1 < slab1) {
+            issue(slab + 1, stage ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();  // slab's segments (and, the first time, the pairs) are visible to every warp
+        const T *sx = reinterpret_cast<const T *>(s_buf + (size_t)stage * a.ucap * kSegBytes) + lane * VEC;
+        const int col = (slab * 32 + lane) * VEC;
+        T uv[VEC], uu[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) uv[k] = uu[k] = (T)0;
+        for (int rr = warp; rr < nrows; rr += kStagedWarps) {
+            int p = s_rp[rr];
+            const int end = s_rp[rr + 1];
+            V acc = VT::zero();
+            for (; p + 3 < end; p += 4) {  // same add order as spmm_gather: ascending permuted source
+                const Pair e0 = s_pairs[p], e1 = s_pairs[p + 1], e2 = s_pairs[p + 2], e3 = s_pairs[p + 3];
+                const V x0 = *reinterpret_cast<const V *>(sx + e0.src * kSegElems);
+                const V x1 = *reinterpret_cast<const V *>(sx + e1.src * kSegElems);
+                const V x2 = *reinterpret_cast<const V *>(sx + e2.src * kSegElems);
+                const V x3 = *reinterpret_cast<const V *>(sx + e3.src * kSegElems);
+                VT::fma(acc, e0.val, x0);
+                VT::fma(acc, e1.val, x1);
+                VT::fma(acc, e2.val, x2);
+                VT::fma(acc, e3.val, x3);
+            }
+            for (; p < end; ++p) {
+                const Pair e = s_pairs[p];
+                VT::fma(acc, e.val, *reinterpret_cast<const V *>(sx + e.src * kSegElems));
+            }
+            const int32_t r = row0 + rr;
+            VT::store(a.Xout + (uint64_t)(uint32_t)r * ld + col, acc);
+            if (EPS) {
+                const T pi = (T)a.stationary[__ldg(a.dest_ids + r)];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const T y = (T)VT::get(acc, k);
+                    uv[k] = fma(y, pi, uv[k]);
+                    uu[k] = fma(y, y, uu[k]);
+                }
+            }
+        }
+        if (EPS) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                s_red[((0 * VEC + k) * kStagedWarps + warp) * 32 + lane] = uv[k];
+                s_red[((1 * VEC + k) * kStagedWarps + warp) * 32 + lane] = uu[k];
+            }
+        }
+        __syncthreads();  // all reads of this stage's buffer are done: the copy issued next iteration may overwrite it
+        if (EPS) {
+            for (int t = threadIdx.x; t < 2 * VEC * 32; t += kStagedWarps * 32) {
+                const int which = t / (VEC * 32), k = (t / 32) % VEC, ln = t & 31;
+                const int gcol = (slab * 32 + ln) * VEC + k;
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < kStagedWarps; ++w) sum += (double)s_red[((which * VEC + k) * kStagedWarps + w) * 32 + ln];
+                atomicAdd(&a.eps_acc[((int64_t)(b % kEpsCopies) * a.ncols + gcol) * 2 + which], sum);
+            }
+            // s_red is rewritten only after the next iteration's first barrier
         }
     }
 }
@@ -582,10 +731,10 @@ template <typename T, int VEC>
 static void launch_gather(const GatherOperand &g, int32_t row_begin, int32_t row_end, const T *in, uint32_t ld_in,
                           T *out, uint32_t ld_out, int32_t ncols, const double *stationary, double *eps_acc,
                           cudaStream_t st, int32_t *sm_counters = nullptr, int32_t num_sms = 0) {
-    static const int rows_per_cta = [] {
-        int r = env_int("CY2P_ROWS_PER_CTA", 32);
-        return r < kWarps ? kWarps : r;
-    }();
+    // rows per CTA: 64 for wide tiles (each warp forms 8 rows; +3% over 32 with the grouped order, 1.31e11 vs 1.27e11
+    // cell-it/s at 50k cells, profiles/k1_sweep7_r01.jsonl), 32 for narrow ones where 64 leaves too few CTAs
+    static const int rows_env = env_int("CY2P_ROWS_PER_CTA", 0);
+    const int rows_per_cta = rows_env > 0 ? std::max(rows_env, kWarps) : (ncols >= 1024 ? 64 : 32);
     GatherArgs<T> a;
     a.t_indptr = g.indptr;
     a.pairs = g.pairs;
@@ -809,6 +958,28 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
         if (rc != CY2P_OK) return rc;
     }
     const bool reord = plan->reorder_state == 1;
+    // Opt-in experiment (CY2P_STAGED=1, read when the plan is ordered and at every call): measured SLOWER than
+    // spmm_gather on B200 — 0.64-0.76e11 vs 1.26e11 cell-it/s at 50k cells (profiles/k1_sweep6_staged_r01.jsonl).
+    // It does cut the L2 -> SM sectors by 45% (197 M vs 357 M per launch), but forming the rows out of shared memory
+    // costs three shared-memory wavefronts and ~6 instructions per 256-byte segment with one CTA of 16 warps per SM,
+    // against one 512-byte LDG.128 and ~10 instructions per segment at 48 warps per SM in the plain kernel.
+    const int staged_env = env_int("CY2P_STAGED", 0);
+    static const int staged_spc = std::max(1, env_int("CY2P_STAGE_SLABS", 8));  // column slabs a CTA walks
+    bool staged = staged_env && reord && plan->nblk > 0;
+    size_t staged_smem = 0;
+    if (staged) {
+        constexpr int SV = kSegBytes / 32 / (int)sizeof(T);
+        staged_smem = 2 * (size_t)plan->blk_ucap * kSegBytes + sizeof(Pair) * kStagedMaxPairs +
+                      sizeof(int32_t) * (kStagedMaxRows + 4) + sizeof(T) * 2 * SV * kStagedWarps * 32;
+        cudaFuncSetAttribute(spmm_staged<T, SV, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(spmm_staged<T, SV, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (staged_smem > 226 * 1024 || plan->blk_ucap > 32 * kStagedWarps ||
+            cudaFuncSetAttribute(spmm_staged<T, SV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem) != cudaSuccess ||
+            cudaFuncSetAttribute(spmm_staged<T, SV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem) != cudaSuccess) {
+            cudaGetLastError();
+            staged = false;
+        }
+    }
     const GatherOperand ident = {plan->d_t_indptr, plan->d_t_pairs, nullptr, 0};
     // SM-affine persistent schedule (experiment, off by default): measured SLOWER than the plain grid on B200
     // (1.01e11 vs 1.23e11 cell-it/s at 50k cells, 0.81e11 vs 1.21e11 at 250k, profiles/k1_sweep5_sm_affine_r01.jsonl):
@@ -857,7 +1028,31 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
                 cnt = counters + slot * kMaxSms;
                 ++launch_no;
             }
-            if (wide && (nc % VW == 0))
+            constexpr int SV = kSegBytes / 32 / (int)sizeof(T);  // elements per lane of the staged kernel
+            if (staged && src_perm && dst_perm && nc % (32 * SV) == 0 && ld_src == ld_dst) {
+                StagedArgs<T> sa;
+                sa.blk_row = plan->d_blk_row;
+                sa.blk_uptr = plan->d_blk_uptr;
+                sa.blk_usrc = plan->d_blk_usrc;
+                sa.r_indptr = plan->d_r_indptr;
+                sa.lpairs = plan->d_r_pairs_lp;
+                sa.dest_ids = plan->d_order;
+                sa.Xin = src;
+                sa.Xout = dst;
+                sa.ld = ld_src;
+                sa.ncols = nc;
+                sa.nslabs = nc / (32 * SV);
+                sa.slabs_per_cta = staged_spc;
+                sa.ucap = plan->blk_ucap;
+                sa.stationary = d_stationary;
+                sa.eps_acc = acc;
+                const dim3 grid((unsigned)plan->nblk, (unsigned)((sa.nslabs + staged_spc - 1) / staged_spc));
+                count_launch();
+                if (acc)
+                    spmm_staged<T, SV, true><<<grid, kStagedWarps * 32, staged_smem, st>>>(sa);
+                else
+                    spmm_staged<T, SV, false><<<grid, kStagedWarps * 32, staged_smem, st>>>(sa);
+            } else if (wide && (nc % VW == 0))
                 launch_gather<T, VW>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms);
             else
                 launch_gather<T, 1>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms);

@@ -355,3 +355,25 @@ def test_batched_convergence_cut_matches_reference_rule(golden):
         assert r["convergence"][b] == (c if (c is not None and c < iters) else iters)
     assert r["convergence"][0] == int(g["convergence"])  # column 0 is the golden run's start
     assert (r["convergence"] < iters).any()
+
+
+def test_staged_gather_experiment_matches_plain(monkeypatch):
+    """The opt-in shared-memory staged gather (CY2P_STAGED=1; slower than the default, kept as a measured
+    experiment) must produce the same iterates and eps as the default gather."""
+    from cy2path_b200.sampling import clear_plan_cache, propagate_batch
+    from cy2path_b200.synth import batched_starts, knn_velocity_tpm, stationary_by_power
+
+    g = knn_velocity_tpm(6000, k=20, seed=17)
+    T = g["T"]
+    X0 = batched_starts(T, 128, seed=2)
+    stat = stationary_by_power(T, 50)
+    clear_plan_cache()
+    ref = propagate_batch(T, X0, 40, stationary=stat)
+    for prec in ("fp32", "fp64"):
+        monkeypatch.setenv("CY2P_STAGED", "1")
+        clear_plan_cache()  # the block lists are built with the plan's ordering
+        got = propagate_batch(T, X0, 40, stationary=stat, precision=prec)
+        monkeypatch.setenv("CY2P_STAGED", "0")
+        assert np.abs(got["final"] - ref["final"]).max() <= 2e-7
+        assert np.abs(got["eps"] - ref["eps"]).max() <= 1e-6
+    clear_plan_cache()
