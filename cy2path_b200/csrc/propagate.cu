@@ -734,7 +734,7 @@ static void launch_gather(const GatherOperand &g, int32_t row_begin, int32_t row
     // rows per CTA: 64 for wide tiles (each warp forms 8 rows; +3% over 32 with the grouped order, 1.31e11 vs 1.27e11
     // cell-it/s at 50k cells, profiles/k1_sweep7_r01.jsonl), 32 for narrow ones where 64 leaves too few CTAs
     static const int rows_env = env_int("CY2P_ROWS_PER_CTA", 0);
-    const int rows_per_cta = rows_env > 0 ? std::max(rows_env, kWarps) : (ncols >= 1024 ? 64 : 32);
+    const int rows_per_cta = rows_env > 0 ? std::max(rows_env, kWarps) : (ncols >= 512 ? 64 : 32);
     GatherArgs<T> a;
     a.t_indptr = g.indptr;
     a.pairs = g.pairs;

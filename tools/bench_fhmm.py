@@ -22,12 +22,13 @@ def main():
     ap.add_argument("--L", type=int, default=4)
     ap.add_argument("--epochs", type=int, default=100)
     ap.add_argument("--unrestricted", action="store_true")
+    ap.add_argument("--model", default="FHMM", choices=["FHMM", "LSSM", "NSSM"])
     ap.add_argument("--oracle", action="store_true", help="also time the oracle's eager torch epoch (GPU + CPU)")
     a = ap.parse_args()
     import torch
 
     from cy2path_b200 import _lib
-    from cy2path_b200.models import FHMM
+    from cy2path_b200 import models
     from cy2path_b200.sampling import get_plan
     from cy2path_b200.synth import knn_velocity_tpm
 
@@ -37,18 +38,19 @@ def main():
     x0 = torch.tensor((g["root_cells"] / g["root_cells"].sum()).astype(np.float32)).cuda()
     D = _lib.propagate(plan, x0, a.I, history_stride=1, want_final=False)["history"].contiguous()
     torch.manual_seed(3)
-    m = FHMM(a.S, a.L, a.N, a.I, restricted=not a.unrestricted, use_gpu=True)
+    m = getattr(models, a.model)(a.S, a.L, a.N, a.I, restricted=not a.unrestricted, use_gpu=True)
+    kind = m._kind
     m.train(D, TPM=T, num_epochs=5)
     torch.cuda.synchronize()
     # kernel-only: loss+grad calls
     params = [p.data for p in m.parameters()]
     w = (1.0, 0.1, 0.1, 0.0)
-    _, _, bufs = _lib.fhmm_loss_grad(plan, *params, D, not a.unrestricted, w)
+    _, _, bufs = _lib.fhmm_loss_grad(plan, *params, D, not a.unrestricted, w, model=kind)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(50):
-        _lib.fhmm_loss_grad(plan, *params, D, not a.unrestricted, w, out=bufs)
+        _lib.fhmm_loss_grad(plan, *params, D, not a.unrestricted, w, out=bufs, model=kind)
     e1.record()
     torch.cuda.synchronize()
     lg_ms = e0.elapsed_time(e1) / 50
@@ -56,7 +58,7 @@ def main():
     m.train(D, TPM=T, num_epochs=a.epochs)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    out = {"N": a.N, "I": a.I, "S": a.S, "L": a.L, "restricted": not a.unrestricted,
+    out = {"model": a.model, "N": a.N, "I": a.I, "S": a.S, "L": a.L, "restricted": not a.unrestricted,
            "loss_grad_ms": lg_ms, "epoch_ms_train_loop": dt / a.epochs * 1e3, "epochs_per_s": a.epochs / dt,
            "cell_iters_per_s": a.N * a.I * a.epochs / dt, "loss_first": m.loss_values[0], "loss_last": m.loss_values[-1],
            "D_bytes": a.N * a.I * 4, "D_pass_GBps": a.N * a.I * 4 / (lg_ms * 1e-3) / 1e9}
