@@ -385,15 +385,23 @@ __host__ __device__ constexpr int next_pow2(int x) { return x <= 1 ? 1 : x <= 2 
 __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x / 2); }
 
 // Thread owns J columns (adjacent column PAIRS share FFMA2 instructions), loops over the rows of its t-split.
+// Slice mode (Rin != nullptr; emission matrices with many rows, see fhmm_data_fwd): the kernel handles rows
+// [koff, koff + K) of the Kfull-row problem, reads r[t,n] = D/P from Rin instead of forming P, and only accumulates
+// the two gradients. Otherwise koff = 0, K = Kfull, ldG = KP.
 template <int KP, int J>
 __global__ void __launch_bounds__(128, (KP <= 12 ? 4 : 1))
 fhmm_data_pass(int N, int I, int K, int tchunk, const float *__restrict__ logE, const float *__restrict__ G,
                const float *__restrict__ D, float *__restrict__ pred, float *__restrict__ glogE_split,
-               float *__restrict__ gG, double *__restrict__ div_acc, float inv_I) {
+               float *__restrict__ gG, double *__restrict__ div_acc, float inv_I, const float *__restrict__ Rin,
+               int koff, int Kfull, int ldG) {
     constexpr int JP = (J + 1) / 2;  // column pairs; J == 1 runs with a dead second half
     extern __shared__ float sG[];    // [tchunk][KP]
     const int t0 = blockIdx.y * tchunk, t1 = min(I, t0 + tchunk);
-    for (int i = threadIdx.x; i < (t1 - t0) * KP; i += blockDim.x) sG[i] = G[(size_t)t0 * KP + i];
+    for (int i = threadIdx.x; i < (t1 - t0) * KP; i += blockDim.x) {
+        const int k = i % KP;
+        sG[i] = k < K ? G[(size_t)(t0 + i / KP) * ldG + koff + k] : 0.f;
+    }
+    logE += (size_t)koff * N;
     const int lane = threadIdx.x & 31;
     const int base = blockIdx.x * blockDim.x * J + threadIdx.x;
     float2 Eh[JP][KP], dE[JP][KP];
@@ -410,7 +418,7 @@ fhmm_data_pass(int N, int I, int K, int tchunk, const float *__restrict__ logE, 
             e[k] = (ok[j] && k < K) ? logE[(size_t)k * N + n] : -INFINITY;
             m = fmaxf(m, e[k]);
         }
-        if (!ok[j]) m = 0.f;
+        if (!ok[j] || Rin != nullptr) m = 0.f;  // slice mode forms no ratio, so it needs no max shift
         mcol[j] = m;
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
@@ -434,13 +442,19 @@ fhmm_data_pass(int N, int I, int K, int tchunk, const float *__restrict__ logE, 
 #pragma unroll
         for (int jp = 0; jp < JP; ++jp) {
             float2 p2 = make_float2(0.f, 0.f);
+            if (Rin == nullptr) {
 #pragma unroll
-            for (int k = 0; k < KP; ++k) p2 = ffma2(g2[k], Eh[jp][k], p2);
+                for (int k = 0; k < KP; ++k) p2 = ffma2(g2[k], Eh[jp][k], p2);
+            }
             float pv[2] = {p2.x, p2.y}, rv[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = 2 * jp + h;
                 const int n = base + j * blockDim.x;
+                if (Rin != nullptr) {  // slice mode: r[t,n] = D/P was formed by fhmm_data_fwd
+                    rv[h] = ok[j] ? __ldg(Rin + (size_t)t * N + n) : 0.f;
+                    continue;
+                }
                 const float d = (ok[j] && D != nullptr) ? __ldg(D + (size_t)t * N + n) : 0.f;
                 const float p = fmaxf(pv[h], FLT_MIN);
                 if (pred != nullptr) {  // forward_model output: full-precision log
@@ -471,16 +485,16 @@ fhmm_data_pass(int N, int I, int K, int tchunk, const float *__restrict__ logE, 
             warp_transpose_reduce<NV>(v, lane);
             constexpr int REP = 32 / NV;  // lanes holding the same element
             const int e = (lane / REP) % NV;
-            if (lane % REP == 0 && e < K && v[0] != 0.f) atomicAdd(&gG[(size_t)t * K + e], -inv_I * v[0]);
+            if (lane % REP == 0 && e < K && v[0] != 0.f) atomicAdd(&gG[(size_t)t * Kfull + koff + e], -inv_I * v[0]);
         } else {
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
                 const float sacc = warp_sum(part2[k].x + part2[k].y);
-                if (lane == 0 && k < K && sacc != 0.f) atomicAdd(&gG[(size_t)t * K + k], -inv_I * sacc);
+                if (lane == 0 && k < K && sacc != 0.f) atomicAdd(&gG[(size_t)t * Kfull + koff + k], -inv_I * sacc);
             }
         }
     }
-    float *out = glogE_split + (size_t)blockIdx.y * K * N;
+    float *out = glogE_split + ((size_t)blockIdx.y * Kfull + koff) * N;
 #pragma unroll
     for (int j = 0; j < 2 * JP; ++j) {
         const int n = base + j * blockDim.x;
@@ -492,6 +506,72 @@ fhmm_data_pass(int N, int I, int K, int tchunk, const float *__restrict__ logE, 
                 const float de = (j & 1) ? dE[j / 2][k].y : dE[j / 2][k].x;
                 out[(size_t)k * N + n] = -inv_I * eh * de;
             }
+    }
+    div = warp_sum(div);
+    __shared__ double sdiv[4];
+    if (lane == 0) sdiv[threadIdx.x >> 5] = div;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(div_acc, (sdiv[0] + sdiv[1] + sdiv[2] + sdiv[3]) * (double)inv_I);
+}
+
+// Emission matrices with many rows (K = S*L > 24: unrestricted FHMM / LSSM, every NSSM): the fused pass above would
+// need 4*K registers per column. The work is split instead: this kernel forms P[t,n] = sum_k G[t,k] E[k,n] over ALL
+// rows (thread = one column pair, K packed FMAs per row of D), writes pred / the divergence and stores
+// r[t,n] = D[t,n] / P[t,n]; fhmm_data_pass then runs once per slice of <= 12 rows in slice mode for the two gradients.
+template <int KP>
+__global__ void __launch_bounds__(128, 3)
+fhmm_data_fwd(int N, int I, int K, int tchunk, const float *__restrict__ logE, const float *__restrict__ G,
+              const float *__restrict__ D, float *__restrict__ pred, float *__restrict__ R,
+              double *__restrict__ div_acc, float inv_I) {
+    extern __shared__ float sG[];  // [tchunk][KP]
+    const int t0 = blockIdx.y * tchunk, t1 = min(I, t0 + tchunk);
+    for (int i = threadIdx.x; i < (t1 - t0) * KP; i += blockDim.x) sG[i] = G[(size_t)t0 * KP + i];
+    const int lane = threadIdx.x & 31;
+    const int base = blockIdx.x * blockDim.x * 2 + threadIdx.x;
+    float2 Eh[KP];
+    float mcol[2], emneg[2];
+    bool ok[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int n = base + j * blockDim.x;
+        ok[j] = n < N;
+        float m = -INFINITY;
+        for (int k = 0; k < K; ++k) m = fmaxf(m, ok[j] ? logE[(size_t)k * N + n] : 0.f);
+        mcol[j] = m;
+        emneg[j] = expf(-m);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const float v = (ok[j] && k < K) ? expf(logE[(size_t)k * N + n] - m) : 0.f;
+            if (j) Eh[k].y = v;
+            else Eh[k].x = v;
+        }
+    }
+    __syncthreads();
+    double div = 0.0;
+    for (int t = t0; t < t1; ++t) {
+        const float *g = sG + (t - t0) * KP;
+        float2 p2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) p2 = ffma2(make_float2(g[k], g[k]), Eh[k], p2);
+        const float pv[2] = {p2.x, p2.y};
+        float div_f = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int n = base + j * blockDim.x;
+            if (!ok[j]) continue;
+            const float p = fmaxf(pv[j], FLT_MIN);
+            if (pred != nullptr) pred[(size_t)t * N + n] = mcol[j] + logf(p);
+            if (D != nullptr) {
+                const float d = __ldg(D + (size_t)t * N + n);
+                float r = 0.f;
+                if (d > 0.f) {
+                    r = __fdividef(d, p) * emneg[j];
+                    div_f += d * (__logf(d) - mcol[j] - __logf(p));
+                }
+                R[(size_t)t * N + n] = r;
+            }
+        }
+        div += (double)div_f;
     }
     div = warp_sum(div);
     __shared__ double sdiv[4];
@@ -1507,6 +1587,10 @@ struct FhmmWs {
     size_t logE, row_lse, hidden, G, small, aux, gG, split, X1, X2, Y1, TP, scal, llv, Hlin, gH, partials, llpart, Apow, total;
     int KP, nsplit, tchunk, P;
     size_t smem_fwd, smem_bwd, smem_local;
+    // emission matrices with more than 24 rows: forward kernel over all rows + gradient slices of 12 rows
+    bool two_pass;
+    int nsplitA, tchunkA;
+    size_t R;
 };
 
 size_t up(size_t x) { return (x + 255) / 256 * 256; }
@@ -1538,18 +1622,27 @@ FhmmWs fhmm_layout(int S, int L, int Le, int N, int I) {
     // t-splits: the data pass runs 128-thread CTAs at 4 per SM (J = 4 variants are register-limited), so aim at
     // whole waves of 148 * 4 CTAs (the first capture ran 1.66 waves: 40% of the second wave idle);
     // the G chunk of a split must fit 32 KB of shared memory
-    const int J = w.KP <= 12 ? 4 : (w.KP <= 24 ? 2 : 1);
-    const int tiles = (N + 128 * J - 1) / (128 * J);
-    const int wave = 148 * 4;
-    int nsplit = tiles >= wave ? 1 : wave / tiles;
-    if (nsplit < 1) nsplit = 1;
-    if (nsplit > I) nsplit = I;
-    int tchunk = (I + nsplit - 1) / nsplit;
-    const int max_chunk = 8192 / (w.KP > 0 ? w.KP : 1);
-    if (tchunk > max_chunk) tchunk = max_chunk;
-    nsplit = (I + tchunk - 1) / tchunk;
-    w.nsplit = nsplit;
-    w.tchunk = tchunk;
+    w.two_pass = w.KP > 24;
+    auto split_for = [&](int J, int kp, int ctas_per_sm, int *nsplit_out, int *tchunk_out) {
+        const int tiles = (N + 128 * J - 1) / (128 * J);
+        const int wave = 148 * ctas_per_sm;
+        int nsplit = tiles >= wave ? 1 : wave / tiles;
+        if (nsplit < 1) nsplit = 1;
+        if (nsplit > I) nsplit = I;
+        int tchunk = (I + nsplit - 1) / nsplit;
+        const int max_chunk = 8192 / (kp > 0 ? kp : 1);
+        if (tchunk > max_chunk) tchunk = max_chunk;
+        *nsplit_out = (I + tchunk - 1) / tchunk;
+        *tchunk_out = tchunk;
+    };
+    if (w.two_pass) {
+        split_for(2, w.KP, 3, &w.nsplitA, &w.tchunkA);
+        split_for(4, 12, 4, &w.nsplit, &w.tchunk);
+    } else {
+        split_for(w.KP <= 12 ? 4 : 2, w.KP, 4, &w.nsplit, &w.tchunk);
+        w.nsplitA = w.tchunkA = 0;
+    }
+    const int nsplit = w.nsplit;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -1575,8 +1668,27 @@ FhmmWs fhmm_layout(int S, int L, int Le, int N, int I) {
     w.partials = take(sizeof(float2) * (size_t)K * ((N + kSoftmaxChunk - 1) / kSoftmaxChunk));
     w.llpart = take(sizeof(double2) * (size_t)((N + 255) / 256));
     w.Apow = take(sizeof(double) * (size_t)w.P * L * S * S);
+    w.R = w.two_pass ? take(sizeof(float) * (size_t)I * N) : 0;
     w.total = off;
     return w;
+}
+
+template <int KP>
+void launch_data_two_pass(int N, int I, int K, const FhmmWs &w, char *ws, const float *logE, const float *G,
+                          const float *D, float *pred, float *split, float *gG, double *div_acc, cudaStream_t st) {
+    float *R = (float *)(ws + w.R);
+    dim3 gridA((unsigned)((N + 255) / 256), (unsigned)w.nsplitA);
+    count_launch();
+    fhmm_data_fwd<KP><<<gridA, 128, sizeof(float) * (size_t)w.tchunkA * KP, st>>>(N, I, K, w.tchunkA, logE, G, D, pred, R,
+                                                                                 div_acc, 1.0f / (float)I);
+    if (D == nullptr) return;  // forward only
+    dim3 gridB((unsigned)((N + 511) / 512), (unsigned)w.nsplit);
+    for (int koff = 0; koff < K; koff += 12) {
+        const int Ks = K - koff < 12 ? K - koff : 12;
+        count_launch();
+        fhmm_data_pass<12, 4><<<gridB, 128, sizeof(float) * (size_t)w.tchunk * 12, st>>>(
+            N, I, Ks, w.tchunk, logE, G, nullptr, nullptr, split, gG, div_acc, 1.0f / (float)I, R, koff, K, KP);
+    }
 }
 
 template <int KP, int J>
@@ -1586,20 +1698,25 @@ void launch_data_pass(int N, int I, int K, const FhmmWs &w, const float *logE, c
     const size_t smem = sizeof(float) * (size_t)w.tchunk * KP;
     count_launch();
     fhmm_data_pass<KP, J><<<grid, 128, smem, st>>>(N, I, K, w.tchunk, logE, G, D, pred, split, gG, div_acc,
-                                                    1.0f / (float)I);
+                                                    1.0f / (float)I, nullptr, 0, K, KP);
 }
 
-void dispatch_data_pass(int N, int I, int K, const FhmmWs &w, const float *logE, const float *G, const float *D,
-                        float *pred, float *split, float *gG, double *div_acc, cudaStream_t st) {
+void dispatch_data_pass(int N, int I, int K, const FhmmWs &w, char *ws, const float *logE, const float *G,
+                        const float *D, float *pred, float *split, float *gG, double *div_acc, cudaStream_t st) {
 #define CASE(KP_, J_)                                                                         \
     case KP_:                                                                                 \
         launch_data_pass<KP_, J_>(N, I, K, w, logE, G, D, pred, split, gG, div_acc, st);      \
         break;
+#define CASE2(KP_)                                                                                \
+    case KP_:                                                                                     \
+        launch_data_two_pass<KP_>(N, I, K, w, ws, logE, G, D, pred, split, gG, div_acc, st);      \
+        break;
     switch (w.KP) {
         CASE(2, 4) CASE(4, 4) CASE(6, 4) CASE(8, 4) CASE(10, 4) CASE(12, 4) CASE(16, 2) CASE(20, 2) CASE(24, 2)
-        CASE(32, 1) CASE(40, 1) CASE(48, 1) CASE(64, 1)
+        CASE2(32) CASE2(40) CASE2(48) CASE2(64)
     }
 #undef CASE
+#undef CASE2
 }
 
 int32_t check_dims(int S, int L, int N, int I, int restricted) {
@@ -1721,7 +1838,7 @@ int32_t lssm_loss_core(cy2p_plan *plan, int S, int L, int Le, int N, int I, int 
     const float *aux = (const float *)(ws + w.f.aux);
     float *X1 = (float *)(ws + w.f.X1), *X2 = (float *)(ws + w.f.X2), *Y1 = (float *)(ws + w.f.Y1),
           *TP = (float *)(ws + w.f.TP);
-    dispatch_data_pass(N, I, K, w.f, logE, (const float *)(ws + w.f.G), d_D, nullptr, (float *)(ws + w.f.split),
+    dispatch_data_pass(N, I, K, w.f, ws, logE, (const float *)(ws + w.f.G), d_D, nullptr, (float *)(ws + w.f.split),
                        (float *)(ws + w.f.gG), scal + sc.div, st);
     const unsigned gN = (unsigned)((N + 127) / 128);
     count_launch();
@@ -1868,7 +1985,7 @@ int32_t cy2p_fhmm_forward(int32_t S, int32_t L, int32_t N, int32_t I, int32_t re
         // pred only: the data pass with D == nullptr (no divergence / gradient contributions)
         CY2P_CUDA(cudaMemsetAsync(ws + w.gG, 0, sizeof(float) * (size_t)I * K, st));
         CY2P_CUDA(cudaMemsetAsync(ws + w.scal, 0, sizeof(double) * ScalarOffsets(S, L, K).total, st));
-        dispatch_data_pass(N, I, K, w, logE, (const float *)(ws + w.G), nullptr, d_pred, (float *)(ws + w.split),
+        dispatch_data_pass(N, I, K, w, ws, logE, (const float *)(ws + w.G), nullptr, d_pred, (float *)(ws + w.split),
                            (float *)(ws + w.gG), (double *)(ws + w.scal), st);
     }
     if (d_hidden)
@@ -1917,7 +2034,7 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
     rc = run_forward(S, L, Le, N, I, restricted, theta_pi, theta_w, theta_E, theta_A, w, ws, st);
     if (rc) return rc;
     // pass over D
-    dispatch_data_pass(N, I, K, w, logE, (const float *)(ws + w.G), d_D, nullptr, (float *)(ws + w.split),
+    dispatch_data_pass(N, I, K, w, ws, logE, (const float *)(ws + w.G), d_D, nullptr, (float *)(ws + w.split),
                        (float *)(ws + w.gG), scal + sc.div, st);
     // node-level conditionals and their products with T
     const unsigned gN = (unsigned)((N + 127) / 128);
@@ -2032,7 +2149,7 @@ int32_t cy2p_lssm_forward(int32_t S, int32_t L, int32_t N, int32_t I, int32_t re
     if (d_pred) {
         CY2P_CUDA(cudaMemsetAsync(ws + w.f.gG, 0, sizeof(float) * (size_t)I * K, st));
         CY2P_CUDA(cudaMemsetAsync(ws + w.f.scal, 0, sizeof(double) * ScalarOffsets(S, L, K).total, st));
-        dispatch_data_pass(N, I, K, w.f, logE, (const float *)(ws + w.f.G), nullptr, d_pred, (float *)(ws + w.f.split),
+        dispatch_data_pass(N, I, K, w.f, ws, logE, (const float *)(ws + w.f.G), nullptr, d_pred, (float *)(ws + w.f.split),
                            (float *)(ws + w.f.gG), (double *)(ws + w.f.scal), st);
     }
     if (d_hidden)
@@ -2137,7 +2254,7 @@ int32_t cy2p_nssm_forward(int32_t S, int32_t L, int32_t N, int32_t I, int32_t re
     if (d_pred) {
         CY2P_CUDA(cudaMemsetAsync(ws + w.l.f.gG, 0, sizeof(float) * (size_t)I * K, st));
         CY2P_CUDA(cudaMemsetAsync(ws + w.l.f.scal, 0, sizeof(double) * ScalarOffsets(S, L, K).total, st));
-        dispatch_data_pass(N, I, K, w.l.f, logEhat, (const float *)(ws + w.l.f.G), nullptr, d_pred,
+        dispatch_data_pass(N, I, K, w.l.f, ws, logEhat, (const float *)(ws + w.l.f.G), nullptr, d_pred,
                            (float *)(ws + w.l.f.split), (float *)(ws + w.l.f.gG), (double *)(ws + w.l.f.scal), st);
     }
     if (d_hidden)

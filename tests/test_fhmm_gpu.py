@@ -75,7 +75,9 @@ def test_loss_terms_and_gradients_match_reference_golden(golden, name):
 
 @pytest.mark.parametrize("kind", ["fhmm", "lssm", "nssm"])
 @pytest.mark.parametrize("S,L,restricted,N,I", [(10, 4, True, 2000, 60), (5, 3, False, 1500, 40), (12, 2, True, 777, 33),
-                                                 (3, 1, False, 300, 9)])
+                                                 (3, 1, False, 300, 9),
+                                                 # more than 24 emission rows: forward kernel + gradient slices
+                                                 (10, 4, False, 1300, 50), (16, 4, False, 640, 21), (9, 3, False, 515, 30)])
 def test_mid_size_vs_oracle_autograd(S, L, restricted, N, I, kind):
     import scipy.sparse as sp
 
