@@ -12,7 +12,7 @@ __version__ = "0.1.0"
 
 __all__ = [
     "iterate_state_probability", "sample_state_probability", "check_convergence_criteria", "propagate_batch",
-    "extract_nonzero_entries", "iterate_markov_chain", "sample_markov_chains", "FHMM", "LSSM", "NSSM", "infer_dynamics",
+    "extract_nonzero_entries", "iterate_markov_chain", "sample_markov_chains", "FHMM", "LSSM", "NSSM", "infer_dynamics", "cluster_markov_chains",
 ]
 
 
@@ -25,4 +25,8 @@ def __getattr__(name):  # lazy: torch.nn is only imported when the model is used
         from .dynamics import infer_dynamics
 
         return infer_dynamics
+    if name == "cluster_markov_chains":
+        from .cytopath import cluster_markov_chains
+
+        return cluster_markov_chains
     raise AttributeError(name)

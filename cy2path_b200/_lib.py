@@ -26,7 +26,7 @@ SYMBOLS = [
     "cy2p_sample_chains", "cy2p_chain_history", "cy2p_fhmm_ws_bytes", "cy2p_fhmm_small_floats",
     "cy2p_fhmm_forward", "cy2p_fhmm_loss_grad", "cy2p_fhmm_decode", "cy2p_lssm_ws_bytes", "cy2p_lssm_small_floats",
     "cy2p_lssm_forward", "cy2p_lssm_loss_grad", "cy2p_lssm_decode", "cy2p_nssm_ws_bytes", "cy2p_nssm_forward",
-    "cy2p_nssm_loss_grad", "cy2p_nssm_decode",
+    "cy2p_nssm_loss_grad", "cy2p_nssm_decode", "cy2p_traj_ws_bytes", "cy2p_dtw_matrix", "cy2p_hausdorff_matrix",
 ]
 
 _lib = None
@@ -97,12 +97,17 @@ def load():
         lib.cy2p_nssm_forward.argtypes = [_i32] * 5 + [_vp] * 11 + [_sz, _vp]
         lib.cy2p_nssm_loss_grad.argtypes = lib.cy2p_fhmm_loss_grad.argtypes
         lib.cy2p_nssm_decode.argtypes = lib.cy2p_fhmm_decode.argtypes
+    if hasattr(lib, "cy2p_dtw_matrix"):
+        lib.cy2p_traj_ws_bytes.argtypes = [_i32, _i32]
+        lib.cy2p_traj_ws_bytes.restype = _sz
+        lib.cy2p_dtw_matrix.argtypes = [_vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]
+        lib.cy2p_hausdorff_matrix.argtypes = lib.cy2p_dtw_matrix.argtypes
     for name in SYMBOLS:
         fn = getattr(lib, name, None)
         if fn is not None and name not in ("cy2p_last_error", "cy2p_propagate_ws_bytes", "cy2p_fhmm_ws_bytes",
                                            "cy2p_fhmm_small_floats", "cy2p_abi_version", "cy2p_launch_count",
                                            "cy2p_propagate_f64_ws_bytes", "cy2p_lssm_ws_bytes",
-                                           "cy2p_lssm_small_floats", "cy2p_nssm_ws_bytes"):
+                                           "cy2p_lssm_small_floats", "cy2p_nssm_ws_bytes", "cy2p_traj_ws_bytes"):
             fn.restype = _i32
     _lib = lib
     return lib
@@ -373,4 +378,32 @@ def fhmm_decode(theta_pi, theta_w, theta_E, theta_A, D, restricted, model="fhmm"
                  ptr(out["log_alpha"]), ptr(out["log_probs"]), ptr(out["log_beta"]), ptr(out["log_gamma"]),
                  ptr(out["log_delta"]), ptr(out["psi"]), ptr(out["log_max"]), ptr(out["best_path"]), ptr(ws), nbytes,
                  stream_ptr(dev)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K4 (trajectory distances)
+def trajectory_distance_matrix(series, kind="dtw"):
+    """cy2p_dtw_matrix / cy2p_hausdorff_matrix. ``series``: cuda float64 tensor [C, len, d] (d <= 64).
+    Returns a cuda float64 tensor [C, C] (symmetric, zero diagonal)."""
+    torch = _torch()
+    lib = load()
+    if kind not in ("dtw", "hausdorff"):
+        raise ValueError("kind must be 'dtw' or 'hausdorff'")
+    if series.dim() != 3 or not series.is_cuda:
+        raise ValueError("series must be a cuda tensor [C, len, d]")
+    C, ln, d = (int(v) for v in series.shape)
+    if d > 64:
+        raise ValueError("at most 64 dimensions per point are supported (reduce the basis, e.g. fewer principal components)")
+    dpad = max(8, (d + 7) // 8 * 8)
+    dev = series.device
+    with torch.cuda.device(dev):
+        s = torch.zeros((C, ln, dpad), dtype=torch.float64, device=dev)
+        s[:, :, :d] = series.to(torch.float64)
+        out = torch.empty((C, C), dtype=torch.float64, device=dev)
+        if C == 0 or ln == 0:
+            return out.zero_()
+        nbytes = lib.cy2p_traj_ws_bytes(C, ln)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        fn = lib.cy2p_dtw_matrix if kind == "dtw" else lib.cy2p_hausdorff_matrix
+        check(fn(ptr(s), C, ln, dpad, ptr(out), ptr(ws), nbytes, stream_ptr(dev)))
     return out

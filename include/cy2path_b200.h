@@ -235,6 +235,19 @@ int32_t cy2p_nssm_decode(int32_t S, int32_t L, int32_t N, int32_t I, int32_t res
                          float *d_log_delta, float *d_psi, float *d_log_max, float *d_best_path, void *d_ws,
                          size_t ws_bytes, void *stream);
 
+/* ---- K4: pairwise distance matrices between sampled trajectories ------------------------------------
+ * Replace dtaidistance.dtw_ndim.distance_matrix_fast (cytopath.py:92-94) and compute_Hausdorff_distance
+ * (cytopath.py:30-45) of the lineage clustering. d_series: float64 device [C][len][dpad], the point dimension
+ * zero-padded to dpad (a multiple of 8, <= 64), 16-byte aligned; d_out: float64 [C][C], symmetric, zero diagonal.
+ *   DTW: squared-Euclidean local cost, D[i][j] = cost + min(D[i-1][j], D[i][j-1], D[i-1][j-1]), sqrt at the end.
+ *   Hausdorff: max(max_a min_b |a-b|, max_b min_a |a-b|), Euclidean.
+ * d_ws >= cy2p_traj_ws_bytes(C, len) bytes. */
+size_t cy2p_traj_ws_bytes(int32_t C, int32_t len);
+int32_t cy2p_dtw_matrix(const double *d_series, int32_t C, int32_t len, int32_t dpad, double *d_out, void *d_ws,
+                        size_t ws_bytes, void *stream);
+int32_t cy2p_hausdorff_matrix(const double *d_series, int32_t C, int32_t len, int32_t dpad, double *d_out,
+                              void *d_ws, size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
