@@ -194,7 +194,7 @@ def run_reference(args, w):
         "e2e": {"value": value, "unit": "cell-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(w, args, world):
@@ -393,13 +393,36 @@ def run_b200(args, w):
                                              if has_chains and chain_ms > 0 else None),
                        "propagate_cell_iterations_per_s": world * cell_iters_per_gpu / (prop_ms_avg * 1e-3)},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line (the driver parses it): everything else a library prints there
+    (the NCCL version banner, for one) is sent to stderr by pointing fd 1 at fd 2 for the run."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse()
+    _claim_stdout()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w)
