@@ -22,7 +22,8 @@ SYMBOLS = [
     "cy2p_plan_info", "cy2p_propagate_ws_bytes", "cy2p_propagate_column_tile", "cy2p_propagate", "cy2p_propagate_rows",
     "cy2p_propagate_f64_ws_bytes", "cy2p_propagate_f64", "cy2p_propagate_rows_f64", "cy2p_plan_order",
     "cy2p_propagate_rows_ordered", "cy2p_propagate_rows_ordered_f64", "cy2p_propagate_rows_allgather",
-    "cy2p_propagate_rows_allgather_f64", "cy2p_enable_peer_access", "cy2p_cdf_build",
+    "cy2p_propagate_rows_allgather_f64", "cy2p_propagate_rows_push", "cy2p_propagate_rows_push_f64",
+    "cy2p_enable_peer_access", "cy2p_cdf_build",
     "cy2p_sample_chains", "cy2p_chain_history", "cy2p_fhmm_ws_bytes", "cy2p_fhmm_small_floats",
     "cy2p_fhmm_forward", "cy2p_fhmm_loss_grad", "cy2p_fhmm_decode", "cy2p_lssm_ws_bytes", "cy2p_lssm_small_floats",
     "cy2p_lssm_forward", "cy2p_lssm_loss_grad", "cy2p_lssm_decode", "cy2p_nssm_ws_bytes", "cy2p_nssm_forward",
@@ -68,6 +69,8 @@ def load():
     lib.cy2p_propagate_rows_ordered_f64.argtypes = lib.cy2p_propagate_rows.argtypes
     lib.cy2p_propagate_rows_allgather.argtypes = [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]
     lib.cy2p_propagate_rows_allgather_f64.argtypes = lib.cy2p_propagate_rows_allgather.argtypes
+    lib.cy2p_propagate_rows_push.argtypes = [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp]
+    lib.cy2p_propagate_rows_push_f64.argtypes = lib.cy2p_propagate_rows_push.argtypes
     lib.cy2p_enable_peer_access.argtypes = [_i32, _i32]
     lib.cy2p_cdf_build.argtypes = [_vp, _vp, _vp, _i32, _vp]
     lib.cy2p_sample_chains.argtypes = [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]

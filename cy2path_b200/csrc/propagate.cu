@@ -112,6 +112,7 @@ struct GatherArgs {
     double *eps_acc;
     T *const *peer_out;
     int32_t npeers;
+    const uint32_t *peer_mask;  // per destination row: bit g set = peer g needs the row (null = every peer)
 };
 
 // Destination rows [row0, row1) x column slab `slab` (32*VEC columns) by one CTA; `copy_sel` picks the eps
@@ -174,7 +175,10 @@ __device__ __forceinline__ void gather_block(const GatherArgs<T> &a, int32_t row
             } else {
                 // fused all-gather (row-partitioned propagation): the finished row goes straight into every rank's
                 // next-iterate buffer — local HBM for this rank, NVLink peer stores for the others
-                for (int32_t g = 0; g < a.npeers; ++g) VT::store(a.peer_out[g] + off, acc);
+                // (halo push: only the ranks whose rows gather this row, `peer_mask`)
+                const uint32_t want = a.peer_mask ? __ldg(a.peer_mask + r) : 0xffffffffu;
+                for (int32_t g = 0; g < a.npeers; ++g)
+                    if ((want >> (g & 31)) & 1u) VT::store(a.peer_out[g] + off, acc);
             }
             if (EPS) {
                 const T pi = (T)a.stationary[cell];
@@ -613,7 +617,8 @@ spmv_b1_cluster_dsmem(int32_t n, const int32_t *__restrict__ t_indptr, const Pai
 template <typename T>
 __global__ void __launch_bounds__(256)
 spmv_rows(int32_t row_begin, int32_t row_end, const int32_t *__restrict__ t_indptr, const Pair *__restrict__ pairs,
-          const T *__restrict__ x, T *__restrict__ y, T *const *__restrict__ peer_out, int32_t npeers) {
+          const T *__restrict__ x, T *__restrict__ y, T *const *__restrict__ peer_out, int32_t npeers,
+          const uint32_t *__restrict__ peer_mask) {
     constexpr int G = 8;
     const int lane = threadIdx.x & 31, gl = lane % G;
     const int32_t r = row_begin + (int32_t)((blockIdx.x * (blockDim.x / G)) + threadIdx.x / G);
@@ -639,7 +644,9 @@ spmv_rows(int32_t row_begin, int32_t row_end, const int32_t *__restrict__ t_indp
         if (peer_out == nullptr) {
             if (gl == 0) y[r] = acc;
         } else {  // every lane of the group holds the sum: lane gl serves peers gl, gl + G, ...
-            for (int32_t g = gl; g < npeers; g += G) peer_out[g][r] = acc;
+            const uint32_t want = peer_mask ? __ldg(peer_mask + r) : 0xffffffffu;
+            for (int32_t g = gl; g < npeers; g += G)
+                if ((want >> (g & 31)) & 1u) peer_out[g][r] = acc;
         }
     }
 }
@@ -725,6 +732,7 @@ struct GatherOperand {
     int32_t out_orig;
     void *const *peer_out = nullptr;  // device array of `npeers` output base pointers (fused all-gather), or null
     int32_t npeers = 0;
+    const uint32_t *peer_mask = nullptr;
 };
 
 template <typename T, int VEC>
@@ -749,6 +757,7 @@ static void launch_gather(const GatherOperand &g, int32_t row_begin, int32_t row
     a.eps_acc = eps_acc;
     a.peer_out = (T *const *)g.peer_out;
     a.npeers = g.npeers;
+    a.peer_mask = g.peer_mask;
     const int nslabs = (ncols + 32 * VEC - 1) / (32 * VEC);
     count_launch();
     if (sm_counters != nullptr && row_begin == 0) {  // persistent SM-affine schedule (counters zeroed by the caller)
@@ -1088,7 +1097,7 @@ static int32_t propagate_rows_impl(cy2p_plan *plan, const T *d_X, T *d_Y, int32_
         const int rows_per_cta = 256 / 8;
         count_launch();
         spmv_rows<T><<<(unsigned)((row_end - row_begin + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(
-            row_begin, row_end, plan->d_t_indptr, plan->d_t_pairs, d_X, d_Y, nullptr, 0);
+            row_begin, row_end, plan->d_t_indptr, plan->d_t_pairs, d_X, d_Y, nullptr, 0, nullptr);
     } else if (B % VW == 0 && aligned16(d_X) && aligned16(d_Y))
         launch_gather<T, VW>(ident, row_begin, row_end, d_X, B, d_Y, B, B, nullptr, nullptr, st);
     else
@@ -1102,10 +1111,11 @@ static int32_t propagate_rows_impl(cy2p_plan *plan, const T *d_X, T *d_Y, int32_
 template <typename T>
 static int32_t propagate_rows_ordered_impl(cy2p_plan *plan, const T *d_Xp, T *d_Yp, int32_t B, int32_t q_begin,
                                            int32_t q_end, void *stream, void *const *d_peer_out = nullptr,
-                                           int32_t npeers = 0) {
+                                           int32_t npeers = 0, const uint32_t *d_peer_mask = nullptr) {
     constexpr int VW = Wide<T>::VEC;
     CY2P_REQUIRE(plan && d_Xp && (d_Yp || d_peer_out), "null pointer");
     CY2P_REQUIRE(!d_peer_out || (npeers >= 1 && npeers <= 64), "1 <= npeers <= 64 required with peer outputs");
+    CY2P_REQUIRE(!d_peer_mask || (d_peer_out && npeers <= 32), "a peer mask needs peer outputs and at most 32 peers");
     CY2P_REQUIRE(B >= 1 && q_begin >= 0 && q_end <= plan->n && q_begin <= q_end, "bad row range / B");
     cudaStream_t st = (cudaStream_t)stream;
     CY2P_CUDA(cudaSetDevice(plan->device));
@@ -1117,11 +1127,12 @@ static int32_t propagate_rows_ordered_impl(cy2p_plan *plan, const T *d_Xp, T *d_
         const int rows_per_cta = 256 / 8;
         count_launch();
         spmv_rows<T><<<(unsigned)((q_end - q_begin + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(
-            q_begin, q_end, ip, pr, d_Xp, d_Yp, (T *const *)d_peer_out, npeers);
+            q_begin, q_end, ip, pr, d_Xp, d_Yp, (T *const *)d_peer_out, npeers, d_peer_mask);
     } else {
         GatherOperand g = {ip, pr, nullptr, 0};  // rows stay in plan order on both sides
         g.peer_out = d_peer_out;
         g.npeers = npeers;
+        g.peer_mask = d_peer_mask;
         if (B % VW == 0 && aligned16(d_Xp) && aligned16(d_Yp))
             launch_gather<T, VW>(g, q_begin, q_end, d_Xp, B, d_Yp, B, B, nullptr, nullptr, st);
         else
@@ -1176,6 +1187,19 @@ int32_t cy2p_propagate_rows_allgather(cy2p_plan *plan, const float *d_Xp, void *
 int32_t cy2p_propagate_rows_allgather_f64(cy2p_plan *plan, const double *d_Xp, void *const *d_peer_out,
                                           int32_t npeers, int32_t B, int32_t q_begin, int32_t q_end, void *stream) {
     return propagate_rows_ordered_impl<double>(plan, d_Xp, nullptr, B, q_begin, q_end, stream, d_peer_out, npeers);
+}
+
+int32_t cy2p_propagate_rows_push(cy2p_plan *plan, const float *d_Xp, void *const *d_peer_out, int32_t npeers,
+                                 const uint32_t *d_row_peers, int32_t B, int32_t q_begin, int32_t q_end, void *stream) {
+    return propagate_rows_ordered_impl<float>(plan, d_Xp, nullptr, B, q_begin, q_end, stream, d_peer_out, npeers,
+                                              d_row_peers);
+}
+
+int32_t cy2p_propagate_rows_push_f64(cy2p_plan *plan, const double *d_Xp, void *const *d_peer_out, int32_t npeers,
+                                     const uint32_t *d_row_peers, int32_t B, int32_t q_begin, int32_t q_end,
+                                     void *stream) {
+    return propagate_rows_ordered_impl<double>(plan, d_Xp, nullptr, B, q_begin, q_end, stream, d_peer_out, npeers,
+                                               d_row_peers);
 }
 
 int32_t cy2p_enable_peer_access(int32_t device, int32_t peer) {

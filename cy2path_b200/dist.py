@@ -139,6 +139,24 @@ def _symmetric_buffers(shape, dtype, dev, group=None):
     if world == 1:
         t = torch.zeros(shape, dtype=dtype, device=dev)
         return t, [t.data_ptr()], (lambda: None)
+    # allocation + rendezvous cost ~100 ms: keep the most recent buffer for repeated calls with the same shape
+    key = (tuple(shape), dtype, str(dev), id(group))
+    if _SYMM_CACHE.get("key") == key:
+        return _SYMM_CACHE["value"]
+    _SYMM_CACHE.clear()
+    value = _symmetric_buffers_new(shape, dtype, dev, group)  # (stores its handle in the cache)
+    _SYMM_CACHE.update(key=key, value=value)
+    return value
+
+
+_SYMM_CACHE = {}
+
+
+def _symmetric_buffers_new(shape, dtype, dev, group=None):
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm
+
     t = symm.empty(shape, dtype=dtype, device=dev)
     hdl = symm.rendezvous(t, group=group if group is not None else dist.group.WORLD)
     t.zero_()
@@ -150,6 +168,7 @@ def _symmetric_buffers(shape, dtype, dev, group=None):
     # stream-ordered cross-rank barrier: a one-element NCCL all-reduce (a rank leaves it only after every rank's
     # preceding kernel, i.e. its peer stores, has completed)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    _SYMM_CACHE["handle"] = hdl  # keeps the peer mappings alive as long as the cached buffer
     return t, ptrs, (lambda: dist.all_reduce(flag, group=group))
 
 
@@ -187,6 +206,80 @@ def propagate_row_partitioned_fused(plan, X0, iters, group=None):
         out = torch.empty_like(out_p)
         out.index_copy_(0, order, out_p)
         barrier()  # nobody releases its buffers while a peer may still be writing
+    return out
+
+
+_MASK_CACHE = {}
+
+
+def row_peer_masks(T, order, world):
+    """For the row partition in the plan's order: uint32 mask per permuted row q, bit g set when rank g needs row q
+    of the iterate — it owns q, or one of its destination rows has q as a source. ``T``: scipy CSR (T[i, j] moves
+    mass from cell i to cell j), ``order``: original cell id at each permuted position. Host-side, once per plan."""
+    import numpy as np
+
+    n = T.shape[0]
+    order = np.asarray(order, dtype=np.int64)
+    pos = np.empty(n, dtype=np.int64)
+    pos[order] = np.arange(n)
+    m, _ = row_blocks(n, world)
+    coo = T.tocoo()
+    src_pos, dst_owner = pos[coo.row], pos[coo.col] // m
+    masks = (np.uint32(1) << (np.arange(n) // m).astype(np.uint32)).astype(np.uint32)
+    for g in range(world):
+        need = np.unique(src_pos[dst_owner == g])
+        masks[need] |= np.uint32(1 << g)
+    return masks
+
+
+def propagate_row_partitioned_halo(plan, T, X0, iters, group=None):
+    """Config-5 driver with a HALO push instead of an all-gather: the update kernel stores a finished row only into
+    the buffers of the ranks that gather it (cy2p_propagate_rows_push with ``row_peer_masks``), over the same
+    symmetric-memory mappings as the fused all-gather. Every rank keeps a full-size iterate of which only its own
+    rows and its halo are current; the final iterate is assembled with one all-gather at the end."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+
+    lib = _lib.load()
+    world, rank = _world(group)
+    if world > 32:
+        raise ValueError("the halo push supports at most 32 ranks")
+    n, B = plan.n, int(X0.shape[1])
+    dev = X0.device
+    order = plan_order(plan)
+    m, blocks = row_blocks(n, world)
+    key = (id(plan), world)
+    if key not in _MASK_CACHE:  # host pass over the stored entries: once per (plan, world)
+        _MASK_CACHE.clear()
+        _MASK_CACHE[key] = torch.from_numpy(row_peer_masks(T, order.cpu().numpy(), world).view("int32")).to(dev)
+    masks = _MASK_CACHE[key]
+    with torch.cuda.device(dev):
+        buf, ptrs, barrier = _symmetric_buffers((2, n, B), X0.dtype, dev, group)
+        half = n * B * X0.element_size()
+        ptr_arrays = [torch.tensor([p + k * half for p in ptrs], dtype=torch.int64, device=dev) for k in range(2)]
+        x0p = X0.index_select(0, order)
+        buf[0].copy_(x0p)
+        fn = lib.cy2p_propagate_rows_push_f64 if X0.dtype.itemsize == 8 else lib.cy2p_propagate_rows_push
+        r0, r1 = blocks[rank]
+        barrier()
+        for it in range(int(iters)):
+            cur, nxt = it & 1, (it + 1) & 1
+            _lib.check(fn(plan.handle, _lib.ptr(buf[cur]), ctypes.c_void_p(ptr_arrays[nxt].data_ptr()), world,
+                          _lib.ptr(masks), B, int(r0), int(r1), _lib.stream_ptr(dev)))
+            barrier()
+        out_p = buf[int(iters) & 1]
+        if world > 1:  # only own rows and halo are current: assemble the whole iterate once
+            full = torch.zeros((m * world, B), dtype=X0.dtype, device=dev)
+            full[rank * m:rank * m + (r1 - r0)].copy_(out_p[r0:r1])
+            dist.all_gather_into_tensor(full, full[rank * m:(rank + 1) * m], group=group)
+            out_p = full[:n]
+        out = torch.empty((n, B), dtype=X0.dtype, device=dev)
+        out.index_copy_(0, order, out_p)
+        barrier()
     return out
 
 

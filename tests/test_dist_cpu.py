@@ -75,3 +75,46 @@ def test_row_partition_and_gather_world2_gloo(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_row_peer_masks_are_sufficient_for_a_halo_exchange():
+    """Emulates the halo push of the row-partitioned mode on the host: every rank keeps a full-size iterate, computes
+    its own rows, and pushes a row only to the ranks named in its mask. The assembled result must equal the unsharded
+    propagation, and the masks must name far fewer rows than an all-gather moves."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+
+    from cy2path_b200.dist import row_blocks, row_peer_masks
+    from cy2path_b200.synth import knn_velocity_tpm
+
+    n, B, iters = 3000, 3, 7
+    g = knn_velocity_tpm(n, k=12, seed=5)
+    T = g["T"].astype(np.float64)
+    order = np.asarray(reverse_cuthill_mckee(sp.csr_matrix(((T + T.T) > 0).astype(np.int8)), symmetric_mode=True))
+    rng = np.random.default_rng(0)
+    X0 = rng.random((n, B))
+    ref = X0.copy()
+    for _ in range(iters):
+        ref = T.T @ ref
+    Tp = sp.csr_matrix(T[order][:, order])  # permuted operator
+    for world in (1, 2, 4, 5):
+        masks = row_peer_masks(g["T"], order, world)
+        assert masks.dtype == np.uint32 and masks.shape == (n,)
+        m, blocks = row_blocks(n, world)
+        bufs = [X0[order].copy() for _ in range(world)]
+        for _ in range(iters):
+            new = [np.full((n, B), np.nan) for _ in range(world)]  # stale rows poison the result if ever read
+            for r, (r0, r1) in enumerate(blocks):
+                rows = (Tp.T.tocsr()[r0:r1] @ np.nan_to_num(bufs[r], nan=np.inf))
+                assert np.isfinite(rows).all()  # every source the rank reads was pushed to it
+                for peer in range(world):
+                    sel = np.nonzero((masks[r0:r1] >> np.uint32(peer)) & np.uint32(1))[0] + r0
+                    new[peer][sel] = rows[sel - r0]
+            bufs = new
+        out_p = np.concatenate([bufs[r][r0:r1] for r, (r0, r1) in enumerate(blocks)])
+        out = np.empty_like(out_p)
+        out[order] = out_p
+        assert np.allclose(out, ref, rtol=1e-12, atol=1e-15), world
+        if world >= 2:
+            pushed = sum(int(((masks >> np.uint32(p)) & np.uint32(1)).sum()) for p in range(world)) - n
+            assert pushed < 0.7 * (world - 1) * n  # the halo is well below the all-gather's (world-1)*n rows

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--f64", type=int, default=0)
     ap.add_argument("--ordered", type=int, default=1)
     ap.add_argument("--fused", type=int, default=0, help="fused update + peer-store all-gather instead of NCCL")
+    ap.add_argument("--halo", type=int, default=0, help="halo push (per-row peer masks) instead of the full exchange")
     ap.add_argument("--cache", default="/tmp/cy2p_config5_graph.npz", help="graph cache on the box (generated once)")
     a = ap.parse_args()
     import torch
@@ -51,6 +52,8 @@ def main():
     if a.f64:
         X0 = X0.double()
     def run(iters):
+        if a.halo:
+            return c2dist.propagate_row_partitioned_halo(plan, T, X0, iters)
         if a.fused:
             return c2dist.propagate_row_partitioned_fused(plan, X0, iters)
         return c2dist.propagate_row_partitioned_cuda(plan, X0, iters, ordered=bool(a.ordered))
@@ -81,7 +84,7 @@ def main():
                           "cell_iterations_per_s": a.n * a.B * a.iters / (ms * 1e-3),
                           "allgather_bytes_per_iter_per_rank": ag_bytes,
                           "allgather_GBps_if_all_time_were_comm": ag_bytes * a.iters / (ms * 1e-3) / 1e9,
-                          "ordered": a.ordered, "fused": a.fused, "mass_checksum": chk, "max_abs_vs_unsharded": err, "dtype": "f64" if a.f64 else "f32"}))
+                          "ordered": a.ordered, "fused": a.fused, "halo": a.halo, "mass_checksum": chk, "max_abs_vs_unsharded": err, "dtype": "f64" if a.f64 else "f32"}))
     if world > 1:
         dist.destroy_process_group()
 
