@@ -377,3 +377,57 @@ def test_staged_gather_experiment_matches_plain(monkeypatch):
         assert np.abs(got["final"] - ref["final"]).max() <= 2e-7
         assert np.abs(got["eps"] - ref["eps"]).max() <= 1e-6
     clear_plan_cache()
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_halo_push_with_virtual_ranks_on_one_gpu(dtype):
+    """cy2p_propagate_rows_push / cy2p_propagate_rows_allgather with the 'peers' being separate buffers on one
+    device: every virtual rank keeps a full-size iterate, computes its own rows and stores a row only where the
+    per-row mask says it is needed (buffers are poisoned with NaN first: a missing push would surface). The assembled
+    result equals the unsharded propagation; world size 1 of the drivers equals it too."""
+    import ctypes
+
+    import torch
+
+    from cy2path_b200 import _lib
+    from cy2path_b200 import dist as c2dist
+    from cy2path_b200.synth import batched_starts, knn_velocity_tpm
+
+    lib = _lib.load()
+    n, iters, world = 4000, 5, 3
+    g = knn_velocity_tpm(n, k=12, seed=29)
+    plan = _lib.Plan(g["T"])
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    for B in (1, 64):
+        X = torch.from_numpy(batched_starts(g["T"], B, seed=4)).cuda().to(tdt)
+        ref = _lib.propagate(plan, X, iters)["final"]
+        tol = 2e-7 if dtype == "float32" else 1e-14
+        assert torch.allclose(c2dist.propagate_row_partitioned_halo(plan, g["T"], X, iters), ref, rtol=0, atol=tol)
+        assert torch.allclose(c2dist.propagate_row_partitioned_fused(plan, X, iters), ref, rtol=0, atol=tol)
+        order = c2dist.plan_order(plan)
+        masks_np = c2dist.row_peer_masks(g["T"], order.cpu().numpy(), world)
+        masks = torch.from_numpy(masks_np.view("int32")).cuda()
+        m, blocks = c2dist.row_blocks(n, world)
+        bufs = [torch.full((2, n, B), float("nan"), dtype=tdt, device="cuda") for _ in range(world)]
+        for b in bufs:
+            b[0].copy_(X.index_select(0, order))
+        fn = lib.cy2p_propagate_rows_push_f64 if dtype == "float64" else lib.cy2p_propagate_rows_push
+        for it in range(iters):
+            cur, nxt = it & 1, (it + 1) & 1
+            ptrs = torch.tensor([b[nxt].data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+            for b in bufs:
+                b[nxt].fill_(float("nan"))
+            for r, (r0, r1) in enumerate(blocks):
+                _lib.check(fn(plan.handle, _lib.ptr(bufs[r][cur]), ctypes.c_void_p(ptrs.data_ptr()), world,
+                              _lib.ptr(masks), B, r0, r1, _lib.stream_ptr(X.device)))
+            torch.cuda.synchronize()
+        fin = iters & 1
+        out_p = torch.cat([bufs[r][fin][r0:r1] for r, (r0, r1) in enumerate(blocks)])
+        assert torch.isfinite(out_p).all()
+        out = torch.empty_like(out_p)
+        out.index_copy_(0, order, out_p)
+        assert torch.allclose(out, ref, rtol=0, atol=tol)
+        # the masks push fewer rows than a full exchange, and un-needed rows really stay untouched (NaN)
+        pushed = sum(int(((masks_np >> np.uint32(p)) & np.uint32(1)).sum()) for p in range(world))
+        assert pushed < world * n
+        assert torch.isnan(bufs[0][fin]).any()
