@@ -252,7 +252,7 @@ def propagate_row_partitioned_halo(plan, T, X0, iters, group=None):
     dev = X0.device
     order = plan_order(plan)
     m, blocks = row_blocks(n, world)
-    key = (id(plan), world)
+    key = (int(plan.handle.value or 0), plan.n, plan.nnz, world)  # the C handle identifies the plan while it lives
     if key not in _MASK_CACHE:  # host pass over the stored entries: once per (plan, world)
         _MASK_CACHE.clear()
         _MASK_CACHE[key] = torch.from_numpy(row_peer_masks(T, order.cpu().numpy(), world).view("int32")).to(dev)
