@@ -8,7 +8,8 @@
 // close together, so the rows gathered by one wave of CTAs form a narrow window of the permuted iterate.
 //
 // A second pass (grow_groups) regroups that order into tight sets of 32 cells that share sources: +3% on the gather
-// (L1 hits between the rows of one CTA) at no run-time cost.
+// (L1 hits between the rows of one CTA) at no run-time cost. Host cost at 50k cells / 1.5 M entries: Cuthill-McKee
+// 46 ms, grouping 68 ms, the two span measurements 15 ms.
 //
 // Built once per plan on the host (O(nnz log k)); rejected when it does not shrink the mean |pos(i) - pos(j)| of the
 // stored entries by at least 20% (an input that is already well ordered keeps its order).
@@ -89,7 +90,10 @@ static void grow_groups(int32_t n, int32_t group, const std::vector<int32_t> &ou
                         const std::vector<int32_t> &in_ptr, const std::vector<Pair> &in_pairs,
                         const std::vector<int32_t> &seed_order, std::vector<int32_t> &order) {
     std::vector<uint8_t> placed(n, 0);
-    std::vector<int32_t> links(n, 0), cand;  // cand: unplaced cells with at least one neighbour in the group
+    std::vector<int32_t> links(n, 0), touched;
+    // bucket[c]: cells pushed when their link count became c (entries go stale when the count moves on or the cell is
+    // placed). The next member is the lowest id among the valid entries of the highest non-empty bucket.
+    std::vector<std::vector<int32_t>> bucket;
     order.clear();
     order.reserve(n);
     size_t seed_ptr = 0;
@@ -97,34 +101,41 @@ static void grow_groups(int32_t n, int32_t group, const std::vector<int32_t> &ou
         while (placed[seed_order[seed_ptr]]) ++seed_ptr;
         int32_t v = seed_order[seed_ptr];
         const size_t first = order.size();
-        cand.clear();
+        touched.clear();
+        int32_t top = 0;
         for (int32_t got = 0; got < group; ++got) {
             placed[v] = 1;
             order.push_back(v);
             auto visit = [&](int32_t u) {
-                if (!placed[u] && links[u]++ == 0) cand.push_back(u);
+                if (placed[u]) return;
+                const int32_t c = ++links[u];
+                if (c == 1) touched.push_back(u);
+                if ((size_t)c >= bucket.size()) bucket.resize((size_t)c + 1);
+                bucket[c].push_back(u);
+                if (c > top) top = c;
             };
             for (int32_t p = out_ptr[v]; p < out_ptr[v + 1]; ++p) visit(out_idx[p]);
             for (int32_t p = in_ptr[v]; p < in_ptr[v + 1]; ++p) visit(in_pairs[p].src);
-            // next member: most links into the group, lowest id on ties. A linear scan over the few hundred candidates
-            // (153 -> 88 ms at 50k cells against a heap with stale entries); placed candidates are compacted away
-            int32_t best = -1, best_links = 0;
-            size_t w = 0;
-            for (size_t r = 0; r < cand.size(); ++r) {
-                const int32_t u = cand[r];
-                if (placed[u]) continue;
-                cand[w++] = u;
-                if (links[u] > best_links || (links[u] == best_links && u < best)) {
-                    best = u;
-                    best_links = links[u];
+            int32_t best = -1;
+            while (top > 0) {
+                std::vector<int32_t> &b = bucket[top];
+                size_t w = 0;
+                for (size_t r = 0; r < b.size(); ++r) {
+                    const int32_t u = b[r];
+                    if (placed[u] || links[u] != top) continue;  // stale
+                    b[w++] = u;
+                    if (best < 0 || u < best) best = u;
                 }
+                b.resize(w);
+                if (best >= 0) break;
+                --top;
             }
-            cand.resize(w);
             if (best < 0) break;  // the component is exhausted: the next group starts from the next seed
             v = best;
         }
-        for (int32_t u : cand) links[u] = 0;
-        for (size_t q = first; q < order.size(); ++q) links[order[q]] = 0;  // members were candidates once
+        for (int32_t u : touched) links[u] = 0;
+        for (size_t q = first; q < order.size(); ++q) links[order[q]] = 0;
+        for (std::vector<int32_t> &b : bucket) b.clear();  // at most max-degree buckets
     }
 }
 
