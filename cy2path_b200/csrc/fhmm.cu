@@ -1,4 +1,6 @@
-// K3 — factorial latent dynamic model (FHMM): forward pass, training loss and ANALYTIC gradients.
+// K3 — latent dynamic models: forward pass, training loss and ANALYTIC gradients, decoders.
+// FHMM first (the north_star's model); LSSM and NSSM (single latent chain with state- / node-level lineage weights,
+// reference models/_LSSM.py, _NSSM.py) reuse its kernels and are found at the end of the device section.
 //
 // Replaces FHMM.forward_model + log_transform_params (reference models/_FHMM.py:84-150,
 // models/methods.py:6-25), compute_log_likelihood (methods.py:28-40) and one epoch's loss + autograd
