@@ -259,9 +259,13 @@ __global__ void __launch_bounds__(512) fhmm_small_forward(int S, int L, int I, i
     }
     __syncthreads();
     // level 3 + hidden = log H
-    for (int i = tid; i < I * SL; i += nt) {
-        const int t = i / SL, sp = (i / L) % S, l = i % L;
-        const int b = t / P, j = t % P;
+    // a thread keeps one (state, lineage) element when the block is a multiple of S*L threads wide and strides over
+    // t, so the index arithmetic of the inner loop is additions only
+    const int l3_groups = nt / SL;
+    const int l3_e = tid % SL, l3_sp = l3_e / L, l3_l = l3_e % L;
+    for (int t = tid / SL; l3_groups > 0 && tid < l3_groups * SL && t < I; t += l3_groups) {
+        const int i = t * SL + l3_e, sp = l3_sp, l = l3_l;
+        const int b = t / P, j = t - b * P;
         double h;
         if (P == 1) {
             h = Hlin[i];  // level 2 already produced every step
@@ -934,7 +938,7 @@ __device__ void write_terms(int S, int L, int K, const double *__restrict__ scal
 __global__ void __launch_bounds__(512)
 fhmm_bwd_local(int S, int L, int I, int P, int restricted, int K, const float *__restrict__ small,
                const float *__restrict__ aux, const float *__restrict__ gG, const double *__restrict__ scal,
-               float *__restrict__ R) {
+               float *__restrict__ R, const double *__restrict__ Hlin, float *__restrict__ gw_acc) {
     const SmallOffsets so(S, L);
     const AuxOffsets ao(S, L);
     const ScalarOffsets sc(S, L, K);
@@ -953,9 +957,11 @@ fhmm_bwd_local(int S, int L, int I, int P, int restricted, int K, const float *_
     const float *Arow = s_A + (l * S + (on ? lane : 0)) * SP;
     const int kidx = restricted ? (on ? lane : 0) : sl;
     const int t_lo = blockIdx.x * P, t_hi = min(I, t_lo + P);
-    float r_next = 0.f;
+    float r_next = 0.f, gw_part = 0.f;  // gw_l = sum_{t,s} gG_t[s,l] H_t[s,l], summed here because the blocks run in parallel
     for (int t = t_hi - 1; t >= t_lo; --t) {
-        const float c = on ? fmaf(wl, gG[(size_t)t * K + kidx], base) : 0.f;
+        const float gg = on ? gG[(size_t)t * K + kidx] : 0.f;
+        if (on) gw_part = fmaf(gg, (float)Hlin[(size_t)t * SL + sl], gw_part);
+        const float c = on ? fmaf(wl, gg, base) : 0.f;
         float a0 = c, a1 = 0.f;
         if (t + 1 < t_hi) {
             int sp = 0;
@@ -969,6 +975,8 @@ fhmm_bwd_local(int S, int L, int I, int P, int restricted, int K, const float *_
         r_next = on ? a0 + a1 : 0.f;
         if (on) R[(size_t)t * SL + sl] = r_next;
     }
+    gw_part = warp_sum(gw_part);
+    if (lane == 0) atomicAdd(&gw_acc[l], gw_part);
 }
 
 __global__ void __launch_bounds__(512)
@@ -976,7 +984,8 @@ fhmm_small_backward(int S, int L, int I, int P, int restricted, int K, const flo
                     const double *__restrict__ Hlin, const double *__restrict__ Apow, const float *__restrict__ aux,
                     const float *__restrict__ gG, const double *__restrict__ scal, float w_sparse, float w_excl,
                     float w_orth, float w_tpm, float *__restrict__ gH /* in: R, out: gH */, float *__restrict__ g_pi,
-                    float *__restrict__ g_w, float *__restrict__ g_A, float *__restrict__ terms) {
+                    float *__restrict__ g_w, float *__restrict__ g_A, float *__restrict__ terms,
+                    const float *__restrict__ gw_acc) {
     const SmallOffsets so(S, L);
     const AuxOffsets ao(S, L);
     const ScalarOffsets sc(S, L, K);
@@ -994,7 +1003,7 @@ fhmm_small_backward(int S, int L, int I, int P, int restricted, int K, const flo
     for (size_t i = tid; i < (size_t)P * L * SS; i += nt) s_pow[(i / S) * SP + i % S] = (float)Apow[i];
     for (int i = tid; i < L; i += nt) {
         s_w[i] = expf(log_w[i]);
-        s_gw[i] = 0.f;
+        s_gw[i] = gw_acc[i];  // summed by fhmm_bwd_local
     }
     __syncthreads();
     // dependent chain over the blocks, one warp per lineage
@@ -1023,12 +1032,11 @@ fhmm_small_backward(int S, int L, int I, int P, int restricted, int K, const flo
         }
     }
     __syncthreads();
-    // gH_t = R_t + A^{e_b - t} Y_b for every (t, s, l), e_b = end of t's block; also gw_l = sum_{t,s} gG_t[s,l] H_t[s,l].
+    // gH_t = R_t + A^{e_b - t} Y_b for every (t, s, l), e_b = end of t's block.
     // Threads are arranged as (group, element): a thread keeps one (s, l) and strides over t.
     {
         const int groups = nt / SL;
         const int gidx = tid / SL, e = tid % SL, s0 = e / L, l = e % L;
-        float gw_part = 0.f;
         if (gidx < groups) {
             for (int t = gidx; t < I; t += groups) {
                 const int b = t / P;
@@ -1044,27 +1052,18 @@ fhmm_small_backward(int S, int L, int I, int P, int restricted, int K, const flo
                 }
                 if (sp < S) a0 = fmaf(Arow[sp], Y[sp * L + l], a0);
                 gH[i] = a0 + a1;
-                gw_part = fmaf(gG[(size_t)t * K + (restricted ? s0 : e)], (float)Hlin[i], gw_part);
             }
-        }
-        s_red[tid] = gw_part;
-        __syncthreads();
-        if (tid < L) {
-            float acc = 0.f;
-            for (int q = 0; q < groups * SL; ++q)
-                if ((q % SL) % L == tid) acc += s_red[q];
-            s_gw[tid] = acc;
         }
         __syncthreads();
     }
     // theta_pi: glogpi = pi * gH_0, softmax over s (per lineage)
-    for (int l = tid; l < L; l += nt) {
-        float dot = 0.f;
-        for (int s0 = 0; s0 < S; ++s0) dot = fmaf(expf(log_pi[s0 * L + l]), gH[s0 * L + l], dot);
-        for (int s0 = 0; s0 < S; ++s0) {
-            const float pi = expf(log_pi[s0 * L + l]);
-            g_pi[s0 * L + l] = pi * gH[s0 * L + l] - pi * dot;
-        }
+    if (warp < L) {  // one warp per lineage, lane = state
+        const int l = warp;
+        const bool on = lane < S;
+        const float pi = on ? expf(log_pi[lane * L + l]) : 0.f;
+        const float pg = on ? pi * gH[lane * L + l] : 0.f;
+        const float dot = warp_sum(pg);
+        if (on) g_pi[lane * L + l] = pg - pi * dot;
     }
     // gA[l,s,s'] = sum_{t=0}^{I-2} H_t[s,l] * gH_{t+1}[s',l]: chunks of t are staged in shared memory (coalesced),
     // every output keeps its own accumulator
@@ -1593,6 +1592,7 @@ struct FhmmWs {
     bool two_pass;
     int nsplitA, tchunkA;
     size_t R;
+    size_t gwacc;  // [kMaxL] floats: dLoss/dw partial sums of fhmm_bwd_local
 };
 
 size_t up(size_t x) { return (x + 255) / 256 * 256; }
@@ -1671,6 +1671,7 @@ FhmmWs fhmm_layout(int S, int L, int Le, int N, int I) {
     w.llpart = take(sizeof(double2) * (size_t)((N + 255) / 256));
     w.Apow = take(sizeof(double) * (size_t)w.P * L * S * S);
     w.R = w.two_pass ? take(sizeof(float) * (size_t)I * N) : 0;
+    w.gwacc = take(sizeof(float) * kMaxL);
     w.total = off;
     return w;
 }
@@ -1876,9 +1877,11 @@ int32_t lssm_loss_core(cy2p_plan *plan, int S, int L, int Le, int N, int I, int 
     const int NB = (I + w.P1 - 1) / w.P1;
     CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_local1));
     count_launch();
+    CY2P_CUDA(cudaMemsetAsync(ws + w.f.gwacc, 0, sizeof(float) * kMaxL, st));
     fhmm_bwd_local<<<NB, 32, w.smem_local1, st>>>(S, 1, I, w.P1, 1, S, (const float *)(ws + w.small1),
                                                   (const float *)(ws + w.aux1), (const float *)(ws + w.gG1), scal1,
-                                                  (float *)(ws + w.f.gH));
+                                                  (float *)(ws + w.f.gH), (const double *)(ws + w.f.Hlin),
+                                                  (float *)(ws + w.f.gwacc));
     CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bwd1));
     float *tmp = (float *)(ws + w.tmp);
     count_launch();
@@ -1886,7 +1889,7 @@ int32_t lssm_loss_core(cy2p_plan *plan, int S, int L, int Le, int N, int I, int 
                                                      (const double *)(ws + w.f.Hlin), (const double *)(ws + w.Apow1),
                                                      (const float *)(ws + w.aux1), (const float *)(ws + w.gG1), scal1,
                                                      w_sparse, 0.f, 0.f, 0.f, (float *)(ws + w.f.gH), d_gpi, tmp,
-                                                     d_gA, tmp + 4);
+                                                     d_gA, tmp + 4, (const float *)(ws + w.f.gwacc));
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }
@@ -2068,16 +2071,18 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
     const int NB = (I + w.P - 1) / w.P;
     CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_local));
     count_launch();
+    CY2P_CUDA(cudaMemsetAsync(ws + w.gwacc, 0, sizeof(float) * kMaxL, st));
     fhmm_bwd_local<<<NB, L * 32, w.smem_local, st>>>(S, L, I, w.P, restricted, K, (const float *)(ws + w.small),
                                                      (const float *)(ws + w.aux), (const float *)(ws + w.gG), scal,
-                                                     (float *)(ws + w.gH));
+                                                     (float *)(ws + w.gH), (const double *)(ws + w.Hlin),
+                                                     (float *)(ws + w.gwacc));
     CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bwd));
     count_launch();
     fhmm_small_backward<<<1, 512, w.smem_bwd, st>>>(S, L, I, w.P, restricted, K, (const float *)(ws + w.small),
                                                     (const double *)(ws + w.Hlin), (const double *)(ws + w.Apow),
                                                     (const float *)(ws + w.aux), (const float *)(ws + w.gG), scal,
                                                     w_sparse, w_excl, w_orth, w_tpm, (float *)(ws + w.gH), d_gpi, d_gw,
-                                                    d_gA, d_terms);
+                                                    d_gA, d_terms, (const float *)(ws + w.gwacc));
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }
