@@ -109,6 +109,7 @@ struct GatherArgs {
     uint32_t ld_out;
     int32_t ncols;
     const double *stationary;
+    const T *pi_rows;  // stationary value of destination row r in the order the rows are walked (iterate precision)
     double *eps_acc;
     T *const *peer_out;
     int32_t npeers;
@@ -132,12 +133,26 @@ __device__ __forceinline__ void gather_block(const GatherArgs<T> &a, int32_t row
     T uv[VEC], uu[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) uv[k] = uu[k] = (T)0;
+    // CTA-wide accumulators of the epilogue: warps add their partials with shared-memory atomics as they finish and the
+    // LAST warp to finish forwards the sums — no barrier at the end of the CTA (a barrier + block reduction there cost
+    // 10% of the kernel: 1.34e11 -> 1.48e11 cell-it/s without it, profiles/README_r01.md §8)
+    __shared__ T s_acc[2][VEC][32];
+    __shared__ unsigned s_done;
+    if (EPS) {
+        for (int t = threadIdx.x; t < 2 * VEC * 32; t += kWarps * 32) (&s_acc[0][0][0])[t] = (T)0;
+        if (threadIdx.x == 0) s_done = 0u;
+        __syncthreads();  // at the start of the CTA, where all warps arrive together
+    }
 
     if (active) {
         const T *__restrict__ xin = a.Xin + col;
         for (int32_t r = row0 + warp; r < row1; r += kWarps) {
             int32_t p = __ldg(a.t_indptr + r);
             const int32_t end = __ldg(a.t_indptr + r + 1);
+            // issued before the gathers so that their latency hides behind them (fetched after the row, the chain
+            // dest id -> stationary value cost 17% of the kernel)
+            const T pi = EPS ? __ldg(a.pi_rows + r) : (T)0;
+            const int32_t orow = a.out_orig ? __ldg(a.dest_ids + r) : r;
             V acc = VT::zero();
             if (p < end && (p & 1)) {  // align the entry cursor to 16 bytes
                 const Pair e = pairs[p];
@@ -168,8 +183,7 @@ __device__ __forceinline__ void gather_block(const GatherArgs<T> &a, int32_t row
                 const Pair e = pairs[p];
                 VT::fma(acc, e.val, VT::load(xin + (uint64_t)(uint32_t)e.src * ld_in));
             }
-            const int32_t cell = a.dest_ids ? __ldg(a.dest_ids + r) : r;
-            const uint64_t off = (uint64_t)(uint32_t)(a.out_orig ? cell : r) * ld_out + col;
+            const uint64_t off = (uint64_t)(uint32_t)orow * ld_out + col;
             if (a.peer_out == nullptr) {
                 VT::store(a.Xout + off, acc);
             } else {
@@ -181,7 +195,6 @@ __device__ __forceinline__ void gather_block(const GatherArgs<T> &a, int32_t row
                     if ((want >> (g & 31)) & 1u) VT::store(a.peer_out[g] + off, acc);
             }
             if (EPS) {
-                const T pi = (T)a.stationary[cell];
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
                     const T y = (T)VT::get(acc, k);
@@ -192,26 +205,25 @@ __device__ __forceinline__ void gather_block(const GatherArgs<T> &a, int32_t row
         }
     }
     if (EPS) {
-        // cross-warp sum through shared memory, laid out [which][k][warp][lane] so that a warp's 32 lanes hit 32
-        // consecutive words (no bank conflicts), then one float64 atomic per (column, which) and CTA
-        __shared__ T red[2][VEC][kWarps][32];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            red[0][k][warp][lane] = uv[k];
-            red[1][k][warp][lane] = uu[k];
+            atomicAdd(&s_acc[0][k][lane], uv[k]);
+            atomicAdd(&s_acc[1][k][lane], uu[k]);
         }
-        __syncthreads();
-        for (int t = threadIdx.x; t < 2 * VEC * 32; t += kWarps * 32) {
-            const int which = t / (VEC * 32), k = (t / 32) % VEC, ln = t & 31;
-            const int gcol = (slab * 32 + ln) * VEC + k;
-            if (gcol < a.ncols) {
-                double s = 0.0;
-#pragma unroll
-                for (int w = 0; w < kWarps; ++w) s += (double)red[which][k][w][ln];
-                atomicAdd(&a.eps_acc[((int64_t)copy_sel * a.ncols + gcol) * 2 + which], s);
+        __threadfence_block();
+        unsigned ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&s_done, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket == kWarps - 1) {  // every warp's partials are in: one float64 atomic per (column, which) and CTA
+            __threadfence_block();
+            for (int t = lane; t < 2 * VEC * 32; t += 32) {
+                const int which = t / (VEC * 32), k = (t / 32) % VEC, ln = t & 31;
+                const int gcol = (slab * 32 + ln) * VEC + k;
+                if (gcol < a.ncols)
+                    atomicAdd(&a.eps_acc[((int64_t)copy_sel * a.ncols + gcol) * 2 + which],
+                              (double)*(volatile T *)&s_acc[which][k][ln]);
             }
         }
-        __syncthreads();  // `red` is reused by the next work item of a persistent CTA
     }
 }
 
@@ -276,6 +288,7 @@ struct StagedArgs {
     uint32_t ld;  // both iterates are scratch tiles with the same pitch
     int32_t ncols, nslabs, slabs_per_cta, ucap;
     const double *stationary;
+    const T *pi_rows;
     double *eps_acc;
 };
 
@@ -360,7 +373,7 @@ __global__ void __launch_bounds__(kStagedWarps * 32, 1) spmm_staged(StagedArgs<T
             const int32_t r = row0 + rr;
             VT::store(a.Xout + (uint64_t)(uint32_t)r * ld + col, acc);
             if (EPS) {
-                const T pi = (T)a.stationary[__ldg(a.dest_ids + r)];
+                const T pi = __ldg(a.pi_rows + r);
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
                     const T y = (T)VT::get(acc, k);
@@ -651,6 +664,14 @@ spmv_rows(int32_t row_begin, int32_t row_end, const int32_t *__restrict__ t_indp
     }
 }
 
+// pi_rows[r] = (T) stationary[dest_ids ? dest_ids[r] : r]: the stationary vector in the order the rows are walked
+template <typename T>
+__global__ void pi_rows_kernel(int32_t n, const double *__restrict__ stationary, const int32_t *__restrict__ dest_ids,
+                               T *__restrict__ out) {
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) out[r] = (T)stationary[dest_ids ? dest_ids[r] : r];
+}
+
 __global__ void sumsq_kernel(int32_t n, const double *__restrict__ v, double *out) {
     double s = 0.0;
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s = fma(v[i], v[i], s);
@@ -699,7 +720,7 @@ static int32_t choose_tile(const cy2p_plan *plan, int32_t B, size_t elem) {
 }
 
 struct WsLayout {
-    size_t eps_acc, vv, bufA, bufB, counters, total;
+    size_t eps_acc, vv, bufA, bufB, counters, pi_id, pi_perm, total;
     int32_t tile;
 };
 constexpr int kCounterSlots = 8192;  // per-launch SM work counters, zeroed in blocks of this many launches
@@ -719,6 +740,10 @@ static WsLayout ws_layout(const cy2p_plan *plan, int32_t B, int32_t iters, size_
     off = align_up(off + elem * (size_t)plan->n * (size_t)w.tile, 256);
     w.counters = off;
     off = align_up(off + sizeof(int32_t) * (size_t)kCounterSlots * kMaxSms, 256);
+    w.pi_id = off;
+    off = align_up(off + elem * (size_t)plan->n, 256);
+    w.pi_perm = off;
+    off = align_up(off + elem * (size_t)plan->n, 256);
     w.total = off;
     return w;
 }
@@ -738,7 +763,8 @@ struct GatherOperand {
 template <typename T, int VEC>
 static void launch_gather(const GatherOperand &g, int32_t row_begin, int32_t row_end, const T *in, uint32_t ld_in,
                           T *out, uint32_t ld_out, int32_t ncols, const double *stationary, double *eps_acc,
-                          cudaStream_t st, int32_t *sm_counters = nullptr, int32_t num_sms = 0) {
+                          cudaStream_t st, int32_t *sm_counters = nullptr, int32_t num_sms = 0,
+                          const T *pi_rows = nullptr) {
     // rows per CTA: 64 for wide tiles (each warp forms 8 rows; +3% over 32 with the grouped order, 1.31e11 vs 1.27e11
     // cell-it/s at 50k cells, profiles/k1_sweep7_r01.jsonl), 32 for narrow ones where 64 leaves too few CTAs
     static const int rows_env = env_int("CY2P_ROWS_PER_CTA", 0);
@@ -754,6 +780,7 @@ static void launch_gather(const GatherOperand &g, int32_t row_begin, int32_t row
     a.ld_out = ld_out;
     a.ncols = ncols;
     a.stationary = stationary;
+    a.pi_rows = pi_rows;
     a.eps_acc = eps_acc;
     a.peer_out = (T *const *)g.peer_out;
     a.npeers = g.npeers;
@@ -967,6 +994,12 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
         if (rc != CY2P_OK) return rc;
     }
     const bool reord = plan->reorder_state == 1;
+    T *pi_rows = nullptr;  // stationary values in the order the destination rows are walked by every launch below
+    if (d_eps) {
+        pi_rows = (T *)(ws + (reord ? w.pi_perm : w.pi_id));
+        count_launch();
+        pi_rows_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(n, d_stationary, reord ? plan->d_order : nullptr, pi_rows);
+    }
     // Opt-in experiment (CY2P_STAGED=1, read when the plan is ordered and at every call): measured SLOWER than
     // spmm_gather on B200 — 0.64-0.76e11 vs 1.26e11 cell-it/s at 50k cells (profiles/k1_sweep6_staged_r01.jsonl).
     // It does cut the L2 -> SM sectors by 45% (197 M vs 357 M per launch), but forming the rows out of shared memory
@@ -1054,6 +1087,7 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
                 sa.slabs_per_cta = staged_spc;
                 sa.ucap = plan->blk_ucap;
                 sa.stationary = d_stationary;
+                sa.pi_rows = pi_rows;
                 sa.eps_acc = acc;
                 const dim3 grid((unsigned)plan->nblk, (unsigned)((sa.nslabs + staged_spc - 1) / staged_spc));
                 count_launch();
@@ -1062,9 +1096,11 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
                 else
                     spmm_staged<T, SV, false><<<grid, kStagedWarps * 32, staged_smem, st>>>(sa);
             } else if (wide && (nc % VW == 0))
-                launch_gather<T, VW>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms);
+                launch_gather<T, VW>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms,
+                                     pi_rows);
             else
-                launch_gather<T, 1>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms);
+                launch_gather<T, 1>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms,
+                                    pi_rows);
             src = dst;
             ld_src = ld_dst;
             src_perm = dst_perm;
