@@ -305,9 +305,9 @@ def run_b200(args, w):
     achieved = bytes_per_launch / launch_s / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed ncu --set full
     # capture of `--workload profile` (same shapes and column tile as config2): profiles/README_r01.md section 5
-    traffic = 958.6e6 if (args.workload in ("config2", "profile") and tile == 2048) else None
+    traffic = 949.2e6 if (args.workload in ("config2", "profile") and tile == 2048) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/ncu_spmm_gather_r01c_raw.csv" if traffic else None, "kernel": "spmv_b1_persistent<double>" if single else "spmm_gather<float,4,true>",
+                "traffic": traffic, "traffic_source": "profiles/ncu_spmm_gather_r01d_raw.csv" if traffic else None, "kernel": "spmv_b1_persistent<double>" if single else "spmm_gather<float,4,true>",
                 "bytes_per_launch": bytes_per_launch,
                 "launch_us": launch_s * 1e6, "launches_per_step": gather_launches, "column_tile": tile,
                 # the resource that actually binds K1: every product needs its own gathered operand,
