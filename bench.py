@@ -311,9 +311,12 @@ def run_b200(args, w):
                 "bytes_per_launch": bytes_per_launch,
                 "launch_us": launch_s * 1e6, "launches_per_step": gather_launches, "column_tile": tile,
                 # the resource that actually binds K1: every product needs its own gathered operand,
-                # nnz x columns x 4 B per update flow L2 -> SM (64 B/clk/SM fill path = 18.2 TB/s at 1.92 GHz)
+                # nnz x columns x 4 B per update flow into the SMs; the part that misses L1 (290.1 M sectors per launch
+                # in the same ncu capture as `traffic`) leaves L2 at its measured output cap (~6,300 B/clk chip-wide,
+                # B300_MICROARCH.md "L2 cache"; 12.1 TB/s at 1.92 GHz)
                 "l2_gather_TBps": (None if single else T.nnz * min(tile, B) * 4 / launch_s / 1e12),
-                "l2_fill_peak_TBps": 148 * 64 * 1.92e9 / 1e12,
+                "l2_to_l1_TBps": (290.1e6 * 32 / launch_s / 1e12 if traffic else None),
+                "lts_cap_TBps": 6300 * 1.92e9 / 1e12,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (sustained copy)" if peaks else "fallback 6650 GB/s"}
 
     # ---- end to end through the public API with host buffers (H2D of T, X0, uniforms; D2H of results)
