@@ -73,6 +73,45 @@ def propagate_batch_sharded(T, X0, iters, stationary=None, tol=1e-5, group=None,
     return res
 
 
+def sample_chains_sharded(T, init_states, uniforms, group=None, walk=None):
+    """Chain-sharded sampling: this rank walks ITS chains — ``init_states`` int32 [C_local],
+    ``uniforms`` float64 [C_local, steps] — with the CDF tables replicated, no collective during the walks; the
+    per-step visit counts are then summed over the ranks (one all-reduce of int32 [steps + 1, n]) and normalised by the
+    total number of chains, so every rank holds the ``state_history_max_iter`` of the whole ensemble
+    (reference simulation.py:156-162: ``counts / counts.sum()`` per step, stored float32).
+
+    ``walk(init_states, uniforms) -> (states [C, steps+1], probs [C, steps])`` replaces the CUDA sampler in the
+    world_size-2 gloo tests only. Returns a dict: ``state_indices`` / ``state_transition_probabilities`` of the local
+    chains, ``state_history_max_iter`` float32 [steps + 1, n] (global), ``num_chains`` (global)."""
+    import torch
+    import torch.distributed as dist
+
+    world, _ = _world(group)
+    n = int(T.shape[0])
+    if walk is None:
+        from .sampling import get_plan
+        from .simulation import _tables_device, _walk
+
+        plan = get_plan(T)
+        idx_d, cum_d = _tables_device(plan)
+        steps = int(np.shape(uniforms)[1])
+        states, probs, _, counts = _walk(plan, idx_d, cum_d, init_states, uniforms, want_history_steps=steps + 1,
+                                         want_counts=True)
+    else:
+        states, probs = walk(init_states, uniforms)
+        states, probs = torch.as_tensor(states), torch.as_tensor(probs)
+        counts = torch.zeros((states.shape[1], n), dtype=torch.int32, device=states.device)
+        counts.scatter_add_(1, states.t().long(), torch.ones_like(states.t(), dtype=torch.int32))
+    total = torch.tensor([int(states.shape[0])], dtype=torch.int64, device=counts.device)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    num_chains = int(total.item())
+    hist = (counts.double() / float(max(num_chains, 1))).float()  # the arithmetic of hist_normalise_kernel (sample.cu)
+    return {"state_indices": states, "state_transition_probabilities": probs, "state_history_max_iter": hist,
+            "num_chains": num_chains}
+
+
 def _cuda_update_rows(plan):
     from . import _lib
 

@@ -41,9 +41,11 @@ def extract_nonzero_entries(adata, matrix_key="T_forward"):
     return idx.cpu().numpy(), cum.cpu().numpy()
 
 
-def _walk(plan, idx_d, cum_d, init_states, uniforms, want_history_steps=None):
+def _walk(plan, idx_d, cum_d, init_states, uniforms, want_history_steps=None, want_counts=False):
     """Run cy2p_sample_chains (+ cy2p_chain_history). init_states int32 [C], uniforms float64 [C, steps]
-    (numpy or cuda tensors). Returns cuda tensors (states [C, steps+1], probs [C, steps], hist or None)."""
+    (numpy or cuda tensors). Returns cuda tensors (states [C, steps+1], probs [C, steps], hist or None);
+    with ``want_counts`` the int32 visit counts behind ``hist`` are returned as a fourth element (the
+    chain-sharded mode sums them over ranks before normalising, dist.sample_chains_sharded)."""
     torch = _lib._torch()
     lib = _lib.load()
     dev = plan.device
@@ -65,12 +67,14 @@ def _walk(plan, idx_d, cum_d, init_states, uniforms, want_history_steps=None):
         _lib.check(lib.cy2p_sample_chains(plan.handle, _lib.ptr(idx_d), _lib.ptr(cum_d), int(idx_d.shape[1]),
                                           _lib.ptr(init_d), _lib.ptr(u_d), C, steps, _lib.ptr(states),
                                           _lib.ptr(probs), _lib.ptr(err), _lib.stream_ptr(dev)))
-        hist = None
+        hist = counts = None
         if want_history_steps:
             counts = torch.empty((want_history_steps, plan.n), dtype=torch.int32, device=dev)
             hist = torch.empty((want_history_steps, plan.n), dtype=torch.float32, device=dev)
             _lib.check(lib.cy2p_chain_history(_lib.ptr(states), C, steps + 1, want_history_steps, plan.n,
                                               _lib.ptr(counts), _lib.ptr(hist), _lib.stream_ptr(dev)))
+    if want_counts:
+        return states, probs, hist, counts
     return states, probs, hist
 
 

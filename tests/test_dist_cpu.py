@@ -70,6 +70,50 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+def _chain_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cy2path_b200.synth import chain_inputs, knn_velocity_tpm
+        from oracle import chains as ochains
+        from oracle import fast as ofast
+
+        g = knn_velocity_tpm(257, k=7, seed=23)
+        T = g["T"]
+        idx, cum = ochains.extract_nonzero_entries(T)
+        C, max_iter = 37, 21  # 19 + 18 chains: uneven shards
+        init_s, uni = chain_inputs(T, g["root_cells"], C, max_iter, seed=3)
+        uni *= float(cum.max(1).min())
+
+        def walk(i, u):  # the oracle's walk stands in for the CUDA sampler
+            return ofast.sample_chains(T, idx, cum, i, u)
+
+        b, e = c2dist.shard_range(C, world, rank)
+        out = c2dist.sample_chains_sharded(T, init_s[b:e], uni[b:e], walk=walk)
+        states, probs = walk(init_s, uni)  # the whole ensemble, unsharded
+        assert out["num_chains"] == C
+        assert np.array_equal(out["state_indices"].numpy(), states[b:e])
+        assert np.array_equal(out["state_transition_probabilities"].numpy().view(np.uint32), probs[b:e].view(np.uint32))
+        ref = np.zeros((max_iter, T.shape[0]), dtype=np.float32)
+        for k in range(max_iter):  # reference simulation.py:156-162
+            ind, cnt = np.unique(states[:, k], return_counts=True)
+            ref[k, ind] = cnt / cnt.sum()
+        hist = out["state_history_max_iter"].numpy()
+        assert hist.dtype == np.float32 and np.array_equal(hist.view(np.uint32), ref.view(np.uint32))
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_chain_sharding_histogram_world2_gloo(tmp_path):
+    """Chains sharded over two ranks: local paths equal the unsharded ones, the all-reduced per-step histogram is
+    bit-equal to the reference's ``counts / counts.sum()`` over the whole ensemble on both ranks."""
+    port = _free_port()
+    mp.spawn(_chain_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
 @pytest.mark.timeout(180)
 def test_row_partition_and_gather_world2_gloo(tmp_path):
     port = _free_port()
