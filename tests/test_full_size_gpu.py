@@ -42,7 +42,7 @@ def test_config2_propagation_properties(graph50k):
     assert torch.isfinite(eps).all() and float(eps.min()) >= 0 and float(eps.max()) <= 2
     pi = torch.from_numpy(stat).cuda()
     cos = 1 - (X.double() * pi[:, None]).sum(0) / torch.sqrt((X.double() ** 2).sum(0) * (pi ** 2).sum())
-    # (per-thread partial sums over 4 rows are fp32, every cross-thread sum is fp64: agreement to a few 1e-8)
+    # (partial sums inside a CTA - 64 rows - are fp32, every sum across CTAs is fp64: agreement to a few 1e-8)
     assert float((eps[-1] - cos.clamp(0, 2)).abs().max()) <= 5e-7
     # batched == the same columns propagated on their own (different tiling / launch shapes)
     cols = [0, 1, 2047, 2048, 4095]
