@@ -2,7 +2,8 @@
 
 Run in the build container only (needs /root/reference):
     python tests/golden/make_golden.py
-Writes small .npz fixtures next to this file. The reference has no golden vectors or tests of
+Writes small .npz fixtures next to this file (or into $CY2P_GOLDEN_OUT: tests/test_golden_reproducible.py
+regenerates them there and compares with the committed files). The reference has no golden vectors or tests of
 its own; these fixtures are outputs of its own functions on seeded synthetic
 inputs and are what pins ``oracle/`` (tests/test_oracle.py) and the CUDA path (tests/test_*_gpu.py).
 """
@@ -13,8 +14,9 @@ import numpy as np
 import pandas as pd
 import torch
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(os.path.dirname(HERE))
+SRC = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(SRC))
+HERE = os.environ.get("CY2P_GOLDEN_OUT", SRC)  # where the fixtures are written
 sys.path.insert(0, ROOT)
 
 from cy2path_b200.synth import knn_velocity_tpm  # noqa: E402
