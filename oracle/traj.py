@@ -14,6 +14,11 @@ version pin (pyproject.toml:39-40, ``hausdorff`` and ``dtaidistance``) and neith
 * ``hausdorff.hausdorff_distance(A, B, distance='euclidean')``: max( max_i min_j |a_i - b_j|,
   max_j min_i |a_i - b_j| ), filled symmetrically by cytopath.py:30-45.
 * ``dtaidistance.preprocessing.differencing(series)``: first differences along the time axis.
+
+Cross-checks that ARE possible here (tests/test_oracle.py): the Hausdorff restatement equals scipy's own
+``scipy.spatial.distance.directed_hausdorff`` (max of the two directions) to 1e-12, and the DTW recurrence equals the
+cheapest monotone lattice path found by scipy's Dijkstra on the explicit DTW graph. The two packages' own outputs
+remain unchecked, hence "unpinned".
 """
 import numpy as np
 

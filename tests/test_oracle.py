@@ -101,3 +101,40 @@ def test_fhmm_oracle_matches_reference(golden, name):
     for t, nme in zip(th, names):
         ref = g["grad_" + nme]
         assert np.abs(t.grad.numpy() - ref).max() <= 1e-5 + 1e-4 * np.abs(ref).max(), nme
+
+
+def test_trajectory_oracle_against_independent_implementations():
+    """oracle/traj.py is "parity unpinned" (dtaidistance / hausdorff are not installed). What CAN be checked on this
+    image: the Hausdorff restatement against scipy's own ``directed_hausdorff`` (third party, same published
+    definition), and the DTW recurrence against an independent formulation — the cheapest monotone lattice path
+    found by scipy's Dijkstra on the explicit DTW graph."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import dijkstra
+    from scipy.spatial.distance import directed_hausdorff
+
+    from oracle import traj as otraj
+
+    rng = np.random.default_rng(11)
+    series = rng.standard_normal((5, 9, 3)).cumsum(1)
+    H = otraj.hausdorff_matrix(series)
+    D = otraj.dtw_matrix(series)
+    assert np.array_equal(H, H.T) and np.array_equal(D, D.T) and not H.diagonal().any() and not D.diagonal().any()
+    for i in range(5):
+        for j in range(i):
+            want = max(directed_hausdorff(series[i], series[j])[0], directed_hausdorff(series[j], series[i])[0])
+            assert abs(H[i, j] - want) <= 1e-12 * max(1.0, want)
+            a, b = series[i], series[j]
+            la, lb = len(a), len(b)
+            cost = ((a[:, None, :] - b[None, :, :]) ** 2).sum(-1)
+            # node (p, q) -> index p * lb + q; an edge INTO a node carries that node's cost; source = a virtual node
+            rows, cols, w = [la * lb], [0], [cost[0, 0]]
+            for p in range(la):
+                for q in range(lb):
+                    for dp, dq in ((1, 0), (0, 1), (1, 1)):
+                        if p + dp < la and q + dq < lb:
+                            rows.append(p * lb + q)
+                            cols.append((p + dp) * lb + q + dq)
+                            w.append(cost[p + dp, q + dq])
+            G = sp.csr_matrix((np.asarray(w) + 1e-300, (rows, cols)), shape=(la * lb + 1, la * lb + 1))
+            best = dijkstra(G, directed=True, indices=la * lb)[la * lb - 1]
+            assert abs(D[i, j] - np.sqrt(best)) <= 1e-10 * max(1.0, D[i, j])
