@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--precision", default="f48", choices=["f48", "f40", "fp64", "fp32"],
+                    help="iterate of the batched propagation (f48 = default of propagate_batch: inside the "
+                         "north_star tolerance at 2,000 iterations; fp32 is outside it beyond ~60)")
     return ap.parse_args()
 
 
@@ -230,9 +233,11 @@ def run_b200(args, w):
     dev = torch.device("cuda", local)
     plan = get_plan(T)
     single = B == 1
+    xprec = (not single) and args.precision in ("f48", "f40")
     X0_d = torch.from_numpy(inp["X0"]).to(dev)
     if single:
         X0_d = X0_d.double().reshape(-1)
+    X0_dd = X0_d.double() if (not single and args.precision == "fp64") else None
     stat_d = torch.from_numpy(inp["stat"]).to(dev)
     has_chains = bool(w["chains"])
     if has_chains:
@@ -249,8 +254,12 @@ def run_b200(args, w):
         e0.record()
         if single:  # sampling.iterate_state_probability: float64 iterate, every iterate kept
             out = _lib.propagate(plan, X0_d, iters, stationary=stat_d, want_final=False, history_stride=1, want_eps=True)
+        elif xprec:
+            out = _lib.propagate_x(plan, X0_d, iters, stationary=stat_d, tail_bits=16 if args.precision == "f48" else 8,
+                                   want_eps=True)
         else:
-            out = _lib.propagate(plan, X0_d, iters, stationary=stat_d, want_final=True, want_eps=True)
+            out = _lib.propagate(plan, X0_dd if args.precision == "fp64" else X0_d, iters, stationary=stat_d,
+                                 want_final=True, want_eps=True)
         e1.record()
         prop_ms.append((e0, e1))
         if has_chains:
@@ -287,7 +296,10 @@ def run_b200(args, w):
     chain_ms = ms_per_step - prop_ms_avg
 
     # ---- roofline of the dominant kernel (spmm_gather): algorithmic bytes per launch / mean launch duration
-    tile = int(lib.cy2p_propagate_column_tile(plan.handle, B))
+    if xprec:
+        tile = int(lib.cy2p_propagate_x_column_tile(plan.handle, B, 16 if args.precision == "f48" else 8))
+    else:
+        tile = int(lib.cy2p_propagate_column_tile(plan.handle, B))
     tiles = (B + tile - 1) // tile
     if single:  # one cooperative launch runs all iterations (float64 iterate: 8-byte elements)
         gather_launches = 1
@@ -305,9 +317,11 @@ def run_b200(args, w):
     achieved = bytes_per_launch / launch_s / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed ncu --set full
     # capture of `--workload profile` (same shapes and column tile as config2): profiles/README_r01.md section 5
-    traffic = 949.2e6 if (args.workload in ("config2", "profile") and tile == 2048) else None
+    traffic = None  # filled from the committed ncu capture of this round's kernel (profiles/)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/ncu_spmm_gather_r01d_raw.csv" if traffic else None, "kernel": "spmv_b1_persistent<double>" if single else "spmm_gather<float,4,true>",
+                "traffic": traffic, "traffic_source": "profiles/ncu_spmm_gather_r01d_raw.csv" if traffic else None, "kernel": ("spmv_b1_persistent<double>" if single else
+                           "spmm_gather_x<%d,...>" % (16 if args.precision == "f48" else 8) if xprec else
+                           "spmm_gather<%s,...>" % ("double" if args.precision == "fp64" else "float")),
                 "bytes_per_launch": bytes_per_launch,
                 "launch_us": launch_s * 1e6, "launches_per_step": gather_launches, "column_tile": tile,
                 # the resource that actually binds K1: every product needs its own gathered operand,
@@ -337,7 +351,7 @@ def run_b200(args, w):
                 r = c2p.iterate_state_probability(ad0, init=inp["X0"][:, 0].astype(np.float64), stationary=inp["stat"],
                                                   max_iter=iters)
             else:
-                r = c2p.propagate_batch(T, inp["X0"], iters, stationary=inp["stat"])
+                r = c2p.propagate_batch(T, inp["X0"], iters, stationary=inp["stat"], precision=args.precision)
             if has_chains:
                 ad = Adata()
                 ad.obsp, ad.shape, ad.uns = {"T_forward": T}, (n, 0), {}
@@ -388,7 +402,8 @@ def run_b200(args, w):
         line = {
             "metric": "msm_cell_iterations_per_s", "value": value, "unit": "cell-iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if single else "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if (single or args.precision != "fp32") else "f32", "data": "synthetic",
             "config": workload_config(w, args, world), "clocks": clocks.summary(), "gpu_launches": int(launches),
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
             "detail": {"propagate_ms_per_step": prop_ms_avg, "chains_ms_per_step": chain_ms,

@@ -21,6 +21,7 @@ SYMBOLS = [
     "cy2p_abi_version", "cy2p_last_error", "cy2p_launch_count", "cy2p_plan_create", "cy2p_plan_create_host", "cy2p_plan_destroy",
     "cy2p_plan_info", "cy2p_propagate_ws_bytes", "cy2p_propagate_column_tile", "cy2p_propagate", "cy2p_propagate_rows",
     "cy2p_propagate_f64_ws_bytes", "cy2p_propagate_f64", "cy2p_propagate_rows_f64", "cy2p_plan_order",
+    "cy2p_propagate_x_ws_bytes", "cy2p_propagate_x_column_tile", "cy2p_propagate_x",
     "cy2p_propagate_rows_ordered", "cy2p_propagate_rows_ordered_f64", "cy2p_propagate_rows_allgather",
     "cy2p_propagate_rows_allgather_f64", "cy2p_propagate_rows_push", "cy2p_propagate_rows_push_f64",
     "cy2p_enable_peer_access", "cy2p_cdf_build",
@@ -65,6 +66,10 @@ def load():
     lib.cy2p_propagate_f64.argtypes = lib.cy2p_propagate.argtypes
     lib.cy2p_propagate_rows_f64.argtypes = lib.cy2p_propagate_rows.argtypes
     lib.cy2p_plan_order.argtypes = [_vp, _vp, _vp]
+    lib.cy2p_propagate_x_ws_bytes.argtypes = [_vp, _i32, _i32, _i32, _i32]
+    lib.cy2p_propagate_x_ws_bytes.restype = _sz
+    lib.cy2p_propagate_x_column_tile.argtypes = [_vp, _i32, _i32]
+    lib.cy2p_propagate_x.argtypes = [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]
     lib.cy2p_propagate_rows_ordered.argtypes = lib.cy2p_propagate_rows.argtypes
     lib.cy2p_propagate_rows_ordered_f64.argtypes = lib.cy2p_propagate_rows.argtypes
     lib.cy2p_propagate_rows_allgather.argtypes = [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]
@@ -258,6 +263,33 @@ def propagate(plan, X0, iters, stationary=None, want_final=True, history_stride=
         hist = hist.reshape(hist.shape[0], plan.n) if hist is not None else None
         eps = eps.reshape(-1) if eps is not None else None
     return {"final": final, "history": hist, "eps": eps}
+
+
+def propagate_x(plan, X0, iters, stationary=None, tail_bits=16, want_eps=False, out_dtype=None):
+    """Run cy2p_propagate_x: batched propagation with the extended-precision ("f48" / "f40") iterate.
+    X0: cuda float32 [n, B]. Returns dict(final, eps): final is float32 (or float64 with out_dtype=torch.float64),
+    eps float64 [iters, B] (bit-reproducible)."""
+    torch = _torch()
+    lib = load()
+    X0 = X0.reshape(plan.n, -1).contiguous()
+    assert X0.dtype == torch.float32 and X0.is_cuda
+    B = X0.shape[1]
+    dev = X0.device
+    f64_out = out_dtype == torch.float64
+    with torch.cuda.device(dev):
+        st = None
+        if stationary is not None:
+            st = torch.as_tensor(np.asarray(stationary, dtype=np.float64) if not torch.is_tensor(stationary)
+                                 else stationary, dtype=torch.float64, device=dev).contiguous()
+        want_eps = bool(want_eps and st is not None)
+        final = torch.empty((plan.n, B), dtype=torch.float64 if f64_out else torch.float32, device=dev)
+        eps = torch.empty((iters, B), dtype=torch.float64, device=dev) if want_eps else None
+        ws_bytes = lib.cy2p_propagate_x_ws_bytes(plan.handle, B, iters, int(want_eps), tail_bits)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.cy2p_propagate_x(plan.handle, ptr(X0), B, iters, ptr(st), None if f64_out else ptr(final),
+                                   ptr(final) if f64_out else None, ptr(eps), tail_bits, ptr(ws), ws_bytes,
+                                   stream_ptr(dev)))
+    return {"final": final, "history": None, "eps": eps}
 
 
 # ------------------------------------------------------------------------------------------ K3 (FHMM)

@@ -37,6 +37,14 @@ struct __align__(8) Pair {
     float val;
 };
 
+// The same entry with the probability widened to float64 (exact): operand of the DFMA in the extended-precision
+// batched update (propagate_x.cu) without a per-product conversion; one 128-bit load.
+struct __align__(16) PairD {
+    int32_t src;
+    int32_t pad;
+    double val;
+};
+
 }  // namespace cy2p
 
 struct cy2p_plan {
@@ -65,6 +73,8 @@ struct cy2p_plan {
     cy2p::Pair *d_r_pairs_pp = nullptr;    // sources as permuted positions  (permuted iterate -> permuted iterate)
     cy2p::Pair *d_r_pairs_op = nullptr;    // sources as original ids        (original iterate -> permuted iterate)
     double span_identity = 0.0, span_reordered = 0.0;  // mean |pos(i) - pos(j)| over the stored entries
+    // float64-valued copies of the three pair arrays (built on first use by propagate_x.cu)
+    cy2p::PairD *d_t_pairsD = nullptr, *d_r_pairsD_pp = nullptr, *d_r_pairsD_op = nullptr;
     // Staged gather (propagate.cu spmm_staged): the permuted rows cut into blocks whose distinct sources fit a CTA's
     // shared memory; sources are named by their index in the block's list
     int32_t nblk = 0;                      // 0 = not built

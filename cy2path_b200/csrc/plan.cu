@@ -172,6 +172,9 @@ static void plan_free(cy2p_plan *p) {
     cudaFree(p->d_blk_uptr);
     cudaFree(p->d_blk_usrc);
     cudaFree(p->d_r_pairs_lp);
+    cudaFree(p->d_t_pairsD);
+    cudaFree(p->d_r_pairsD_pp);
+    cudaFree(p->d_r_pairsD_op);
     delete p;
 }
 

@@ -210,6 +210,7 @@ __device__ __forceinline__ void gather_block(const GatherArgs<T> &a, int32_t row
             atomicAdd(&s_acc[0][k][lane], uv[k]);
             atomicAdd(&s_acc[1][k][lane], uu[k]);
         }
+        __syncwarp();  // every lane's shared-memory atomics are issued before lane 0 takes the ticket
         __threadfence_block();
         unsigned ticket = 0;
         if (lane == 0) ticket = atomicAdd(&s_done, 1u);

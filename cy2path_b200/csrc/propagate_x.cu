@@ -1,0 +1,650 @@
+// K1x — batched MSM propagation  X <- X . T  with an EXTENDED-PRECISION iterate (reference sampling.py:33,38-45).
+//
+// Why: the reference multiplies a float64 iterate by the float32 T in float64 (scipy upcasts). The float32-rounded
+// rows of T do not sum to exactly 1, so on absorbing regions the reference's iterate grows by ~1e-8 per step; a
+// float32 iterate cannot represent that growth (it rounds away every step) and drifts linearly from the reference:
+// relative L1 3.9e-5 after 2,000 iterations, and the float32 FMA chain of the row sum does the same even when the
+// iterate is stored wider (tools/precision_lab.py). The north_star's bar is 1e-6. What holds it is (i) products and
+// row sums in float64 and (ii) an iterate with >= 28 mantissa bits.
+//
+// Format "f48" / "f40" (truncated float64): an element is the top 32 bits of its float64 pattern (sign, 11-bit
+// exponent, 20 mantissa bits: the HEAD) plus the next 16 / 8 mantissa bits (the TAIL), rounded to nearest: 36 / 28
+// mantissa bits in 6 / 5 bytes instead of 8. The head IS the high word of a double and the tail, shifted to the top of
+// the low word, is the rest, so a gathered operand becomes a DFMA operand with ONE integer instruction per element and
+// no conversion (F2F runs at a quarter of the DFMA rate). The kernel is bound by the bytes it moves from L2 into the
+// SMs (profiles/README_r02.md), so 6 bytes instead of 8 is 25% less of the binding traffic.
+//
+// Layout of an iterate tile in the work space: row r, column slab s (32*CPL columns) is one contiguous record
+//   [ heads: 32*CPL x uint32 | tails: 32*CPL x uint16 (uint8) ]      768 (640) bytes at CPL = 4
+// so a warp's gather of one source is one LDG.128 + one LDG.64 (LDG.32) per lane from one contiguous span.
+//
+// eps (sampling.py:44-45) is deterministic here: per-thread float64 partial sums over the thread's rows in a fixed
+// order, then 64-bit FIXED-POINT integer atomics (integer addition is associative, so the order in which warps and
+// CTAs arrive cannot change a bit of the result) — see eps_scale_kernel for the scale.
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace cy2p {
+
+constexpr int kXEpsCopies = 4;  // spread of the global integer accumulators (same-address atomics serialise in L2)
+
+template <int LOB, int CPL>
+struct XFmt {
+    static constexpr int kHiBytes = 32 * CPL * 4;
+    static constexpr int kLoBytes = 32 * CPL * LOB / 8;
+    static constexpr int kRec = kHiBytes + kLoBytes;  // bytes of one (row, slab) record
+    static constexpr int kCols = 32 * CPL;
+};
+
+struct XArgs {
+    const int32_t *indptr;
+    const PairD *pairs;
+    const int32_t *dest_ids;  // original cell id of walked row r (null: identity)
+    int32_t out_orig;         // float outputs: write row dest_ids[r] instead of r
+    const unsigned char *xin;  // f48 tile
+    uint32_t pitch_in;         // bytes per row of the input tile
+    const float *fin;          // float32 input (first update), leading dimension ld_in
+    uint32_t ld_in;
+    unsigned char *xout;
+    uint32_t pitch_out;
+    float *fout;   // float32 output (last update), may be null
+    double *dout;  // float64 output (last update), may be null
+    uint32_t ld_out;
+    int32_t ncols;
+    int32_t wide_io;  // float input/output rows are 16-byte aligned and ncols % 4 == 0
+    const double *pi_rows;
+    unsigned long long *eps_acc;  // [kXEpsCopies][ncols][2] fixed-point sums of this update
+    const double *eps_scale;      // device scalar
+};
+
+__device__ __forceinline__ double mk_double(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
+
+// base + row * pitch as ONE IMAD.WIDE.U32 with a 64-bit addend (left to itself the compiler adds the lane offset in
+// the multiply-add and the uniform base pointer with two more adds)
+__device__ __forceinline__ const unsigned char *row_ptr(const unsigned char *base, uint32_t row, uint32_t pitch) {
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(row), "r"(pitch), "l"((uint64_t)base));
+    return reinterpret_cast<const unsigned char *>(r);
+}
+
+// ---- operand loads: CPL doubles of one source row for this lane ---------------------------------------------------
+// Record of (row, slab): heads as CPL/4 planes of 32 x uint4 (CPL = 2: one plane of 32 x uint2), then the tails,
+// CPL*LOB/8 bytes per lane. Lane `lane` owns columns (slab*32 + lane)*CPL + k, k < CPL.
+template <int LOB, int CPL>
+struct XLoad {
+    static constexpr int kLoWords = (CPL * LOB + 31) / 32;
+    uint32_t h[CPL];
+    uint32_t l[kLoWords];
+    // hi: record + lane * (CPL >= 4 ? 16 : 8);  lo: record + kHiBytes + lane * (CPL*LOB/8)
+    __device__ __forceinline__ void issue(const unsigned char *hi, const unsigned char *lo) {
+        if constexpr (CPL == 2) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(hi));
+            h[0] = v.x, h[1] = v.y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPL / 4; ++j) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(hi + j * 512));
+                h[4 * j] = v.x, h[4 * j + 1] = v.y, h[4 * j + 2] = v.z, h[4 * j + 3] = v.w;
+            }
+        }
+        if constexpr (CPL * LOB == 16) {
+            l[0] = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(lo));
+        } else if constexpr (CPL * LOB == 32) {
+            l[0] = __ldg(reinterpret_cast<const uint32_t *>(lo));
+        } else if constexpr (CPL * LOB == 64) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(lo));
+            l[0] = v.x, l[1] = v.y;
+        } else {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(lo));
+            l[0] = v.x, l[1] = v.y, l[2] = v.z, l[3] = v.w;
+        }
+    }
+    // the tail of element k moved to the top of a float64's low word: one integer instruction
+    __device__ __forceinline__ uint32_t low_word(int k) const {
+        if constexpr (LOB == 16) {
+            return (k & 1) ? (l[k / 2] & 0xffff0000u) : (l[k / 2] << 16);
+        } else {
+            const uint32_t w = l[k / 4];
+            switch (k & 3) {
+                case 0: return w << 24;
+                case 1: return __byte_perm(w, 0u, 0x1444);
+                case 2: return __byte_perm(w, 0u, 0x2444);
+                default: return w & 0xff000000u;
+            }
+        }
+    }
+    __device__ __forceinline__ void fma(double v, double *acc) const {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) acc[k] = ::fma(v, mk_double(low_word(k), h[k]), acc[k]);
+    }
+};
+
+// float32 input row (first update): exact widening, CPL values per lane
+template <int CPL>
+struct FLoad {
+    float x[CPL];
+    __device__ __forceinline__ void issue(const float *p, int nvalid, bool wide) {
+        if (wide) {
+            if constexpr (CPL == 2) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+                x[0] = v.x, x[1] = v.y;
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPL / 4; ++j) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(p + 4 * j));
+                    x[4 * j] = v.x, x[4 * j + 1] = v.y, x[4 * j + 2] = v.z, x[4 * j + 3] = v.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) x[k] = k < nvalid ? __ldg(p + k) : 0.f;
+        }
+    }
+    __device__ __forceinline__ void fma(double v, double *acc) const {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) acc[k] = ::fma(v, (double)x[k], acc[k]);
+    }
+};
+
+// round a float64 to the stored format: keep LOB bits of the low word, nearest (ties away from zero)
+template <int LOB>
+__device__ __forceinline__ void x_round(double y, uint32_t &hi, uint32_t &tail, double &yr) {
+    constexpr int drop = 32 - LOB;
+    long long b = __double_as_longlong(y);
+    b += (1LL << (drop - 1));
+    hi = (uint32_t)((unsigned long long)b >> 32);
+    const uint32_t low = (uint32_t)b;
+    tail = low >> drop;
+    yr = mk_double(low & ~((1u << drop) - 1u), hi);
+}
+
+template <int LOB, int CPL, int WARPS, bool IN_F32, bool OUT_F32, bool EPS>
+__device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int32_t row1, int slab, int copy_sel,
+                                               unsigned long long (*s_acc)[CPL][32], unsigned *s_done) {
+    using F = XFmt<LOB, CPL>;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = (slab * 32 + lane) * CPL;
+    const bool active = col < a.ncols;
+    const int nvalid = min(CPL, a.ncols - col);
+    double uv[CPL], uu[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) uv[k] = uu[k] = 0.0;
+    if (EPS) {
+        for (int t = threadIdx.x; t < 2 * CPL * 32; t += WARPS * 32) (&s_acc[0][0][0])[t] = 0ull;
+        if (threadIdx.x == 0) *s_done = 0u;
+        __syncthreads();
+    }
+    if (active) {
+        const PairD *__restrict__ pairs = a.pairs;
+        const unsigned char *xhi = a.xin + (size_t)slab * F::kRec + lane * (CPL >= 4 ? 16 : 8);
+        const unsigned char *xlo = a.xin + (size_t)slab * F::kRec + F::kHiBytes + lane * (CPL * LOB / 8);
+        const float *fin = a.fin + col;
+        const bool wide = a.wide_io != 0;
+        const uint32_t pitch_in = a.pitch_in;
+        for (int32_t r = row0 + warp; r < row1; r += WARPS) {
+            int32_t p = __ldg(a.indptr + r);
+            const int32_t end = __ldg(a.indptr + r + 1);
+            const double pi = EPS ? __ldg(a.pi_rows + r) : 0.0;
+            const int32_t orow = (OUT_F32 && a.out_orig) ? __ldg(a.dest_ids + r) : r;
+            double acc[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) acc[k] = 0.0;
+            constexpr int U = CPL >= 8 ? 2 : 4;  // row gathers in flight per warp
+            for (; p + U - 1 < end; p += U) {
+                uint4 q[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) q[u] = __ldg(reinterpret_cast<const uint4 *>(pairs + p + u));
+                if (IN_F32) {
+                    FLoad<CPL> x[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) x[u].issue(fin + (uint64_t)q[u].x * a.ld_in, nvalid, wide);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) x[u].fma(mk_double(q[u].z, q[u].w), acc);
+                } else {
+                    XLoad<LOB, CPL> x[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) x[u].issue(row_ptr(xhi, q[u].x, pitch_in), row_ptr(xlo, q[u].x, pitch_in));
+#pragma unroll
+                    for (int u = 0; u < U; ++u) x[u].fma(mk_double(q[u].z, q[u].w), acc);
+                }
+            }
+            for (; p < end; ++p) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(pairs + p));
+                if (IN_F32) {
+                    FLoad<CPL> x;
+                    x.issue(fin + (uint64_t)q.x * a.ld_in, nvalid, wide);
+                    x.fma(mk_double(q.z, q.w), acc);
+                } else {
+                    XLoad<LOB, CPL> x;
+                    x.issue(row_ptr(xhi, q.x, pitch_in), row_ptr(xlo, q.x, pitch_in));
+                    x.fma(mk_double(q.z, q.w), acc);
+                }
+            }
+            // ---- store the row in the stored format (or as float32 / float64 on the last update)
+            uint32_t hi[CPL], tl[CPL];
+            double yr[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) x_round<LOB>(acc[k], hi[k], tl[k], yr[k]);
+            if (OUT_F32) {
+                const uint64_t off = (uint64_t)(uint32_t)orow * a.ld_out + col;
+                if (a.fout) {
+                    if (wide) {
+                        if constexpr (CPL == 2) {
+                            *reinterpret_cast<float2 *>(a.fout + off) = make_float2((float)acc[0], (float)acc[1]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CPL / 4; ++j)
+                                *reinterpret_cast<float4 *>(a.fout + off + 4 * j) = make_float4(
+                                    (float)acc[4 * j], (float)acc[4 * j + 1], (float)acc[4 * j + 2], (float)acc[4 * j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k)
+                            if (k < nvalid) a.fout[off + k] = (float)acc[k];
+                    }
+                }
+                if (a.dout) {
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k)
+                        if (k < nvalid) a.dout[off + k] = acc[k];
+                }
+            } else {
+                unsigned char *rec = a.xout + (uint64_t)(uint32_t)r * a.pitch_out + (size_t)slab * F::kRec;
+                unsigned char *ohi = rec + lane * (CPL >= 4 ? 16 : 8), *olo = rec + F::kHiBytes + lane * (CPL * LOB / 8);
+                if constexpr (CPL == 2) {
+                    *reinterpret_cast<uint2 *>(ohi) = make_uint2(hi[0], hi[1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CPL / 4; ++j)
+                        *reinterpret_cast<uint4 *>(ohi + j * 512) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                }
+                constexpr int LW = (CPL * LOB + 31) / 32;
+                uint32_t lw[LW];
+#pragma unroll
+                for (int j = 0; j < LW; ++j) lw[j] = 0u;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) lw[k * LOB / 32] |= tl[k] << ((k * LOB) % 32);
+                if constexpr (CPL * LOB == 16)
+                    *reinterpret_cast<unsigned short *>(olo) = (unsigned short)lw[0];
+                else if constexpr (CPL * LOB == 32)
+                    *reinterpret_cast<uint32_t *>(olo) = lw[0];
+                else if constexpr (CPL * LOB == 64)
+                    *reinterpret_cast<uint2 *>(olo) = make_uint2(lw[0], lw[1]);
+                else
+                    *reinterpret_cast<uint4 *>(olo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+            if (EPS) {
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const double y = (k < nvalid) ? yr[k] : 0.0;
+                    uv[k] = ::fma(y, pi, uv[k]);
+                    uu[k] = ::fma(y, y, uu[k]);
+                }
+            }
+        }
+    }
+    if (EPS) {
+        const double sc = __ldg(a.eps_scale);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            atomicAdd(&s_acc[0][k][lane], (unsigned long long)__double2ll_rn(uv[k] * sc));
+            atomicAdd(&s_acc[1][k][lane], (unsigned long long)__double2ll_rn(uu[k] * sc));
+        }
+        __syncwarp();
+        __threadfence_block();
+        unsigned ticket = 0;
+        if (lane == 0) ticket = atomicAdd(s_done, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket == WARPS - 1) {  // every warp's partials are in: one integer atomic per (column, which) and CTA
+            __threadfence_block();
+            for (int t = lane; t < 2 * CPL * 32; t += 32) {
+                const int which = t / (CPL * 32), k = (t / 32) % CPL, ln = t & 31;
+                const int gcol = (slab * 32 + ln) * CPL + k;
+                if (gcol < a.ncols)
+                    atomicAdd(&a.eps_acc[((int64_t)copy_sel * a.ncols + gcol) * 2 + which],
+                              *(volatile unsigned long long *)&s_acc[which][k][ln]);
+            }
+        }
+    }
+}
+
+// resident CTAs per SM the register budget is compiled for (8 columns per lane keep 16 float64 accumulators and, with
+// eps, 32 registers of partial sums: 128 registers, 16 warps per SM)
+template <int WARPS, int CPL>
+struct XOcc {
+    static constexpr int kMinBlocks = CPL >= 8 ? (WARPS <= 8 ? 2 : 1) : (WARPS <= 8 ? 3 : (WARPS <= 16 ? 2 : 1));
+};
+
+template <int LOB, int CPL, int WARPS, bool IN_F32, bool OUT_F32, bool EPS>
+__global__ void __launch_bounds__(WARPS * 32, XOcc<WARPS, CPL>::kMinBlocks)
+spmm_gather_x(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, XArgs a) {
+    __shared__ unsigned long long s_acc[2][CPL][32];
+    __shared__ unsigned s_done;
+    const int32_t row0 = row_begin + blockIdx.x * rows_per_cta;
+    gather_block_x<LOB, CPL, WARPS, IN_F32, OUT_F32, EPS>(a, row0, min(row0 + rows_per_cta, row_end), blockIdx.y,
+                                                          blockIdx.x % kXEpsCopies, s_acc, &s_done);
+}
+
+// ---- small kernels ----------------------------------------------------------------------------------------------
+__global__ void widen_pairs_kernel(int64_t nnz, const Pair *__restrict__ in, PairD *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) {
+        const Pair e = in[i];
+        out[i] = PairD{e.src, 0, (double)e.val};
+    }
+}
+
+__global__ void x_pi_rows_kernel(int32_t n, const double *__restrict__ stationary, const int32_t *__restrict__ dest_ids,
+                                 double *__restrict__ out) {
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) out[r] = stationary[dest_ids ? dest_ids[r] : r];
+}
+
+// |x0| column sums in a fixed order: part[chunk][c] = sum over the chunk's rows (ascending), one thread per column
+constexpr int kScaleChunks = 64;
+__global__ void x_colsum_kernel(int32_t n, int32_t B, const float *__restrict__ X0, double *__restrict__ part) {
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= B) return;
+    const int32_t per = (n + kScaleChunks - 1) / kScaleChunks;
+    const int32_t r0 = min(n, (int32_t)blockIdx.y * per), r1 = min(n, r0 + per);
+    double s = 0.0;
+    for (int32_t r = r0; r < r1; ++r) s += fabs((double)X0[(size_t)r * B + c]);
+    part[(size_t)blockIdx.y * B + c] = s;
+}
+
+// One CTA: m = max_c sum_i |x0[i,c]|, pmax = max_i |pi_i|, vv = sum pi^2 (fixed order), and the fixed-point scale
+//   scale = 2^(56 - ceil(log2(max(m*pmax, m*m)))):  the sums of x.pi and x.x stay below 2^56, with 2^7 of headroom in
+// the signed 64-bit accumulators for iterates whose mass grows over the run (T row sums within rounding of 1 give
+// (1 + 1e-7)^iters), at a resolution of 2^-56 of the bound per partial sum.
+__global__ void __launch_bounds__(1024) eps_scale_kernel(int32_t n, int32_t B, const double *__restrict__ part,
+                                                          const double *__restrict__ stationary, double *out_scale,
+                                                          double *out_vv) {
+    __shared__ double s_m[32], s_p[32], s_v[1024];
+    double m = 0.0, pm = 0.0, v = 0.0;
+    for (int32_t c = threadIdx.x; c < B; c += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < kScaleChunks; ++k) s += part[(size_t)k * B + c];
+        m = fmax(m, s);
+    }
+    // vv in a fixed order: thread t sums elements t, t+1024, ...; then a fixed tree
+    for (int32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double p = stationary[i];
+        pm = fmax(pm, fabs(p));
+        v = ::fma(p, p, v);
+    }
+    s_v[threadIdx.x] = v;
+    for (int o = 16; o; o >>= 1) {
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+    }
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m, s_p[threadIdx.x >> 5] = pm;
+    __syncthreads();
+    for (int w = 512; w; w >>= 1) {
+        if ((int)threadIdx.x < w) s_v[threadIdx.x] += s_v[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 32; ++k) m = fmax(m, s_m[k]), pm = fmax(pm, s_p[k]);
+        double bound = fmax(m * pm, m * m);
+        if (!(bound > 0.0) || !isfinite(bound)) bound = 1.0;
+        int e;
+        frexp(bound, &e);  // bound = f * 2^e, f in [0.5, 1)  ->  bound <= 2^e
+        *out_scale = ldexp(1.0, 56 - e);
+        *out_vv = s_v[0];
+    }
+}
+
+// eps[i] = clip(1 - uv/sqrt(uu*vv), 0, 2) from the integer sums (copies added as integers: order-free)
+__global__ void x_eps_finalize(int32_t iters, int32_t tile_cols, int32_t col0, int32_t B,
+                               const unsigned long long *__restrict__ acc, const double *__restrict__ scale,
+                               const double *__restrict__ vv, double *__restrict__ eps) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)iters * tile_cols) return;
+    const int32_t it = (int32_t)(i / tile_cols), c = (int32_t)(i % tile_cols);
+    const unsigned long long *a = acc + ((int64_t)it * kXEpsCopies * tile_cols + c) * 2;
+    unsigned long long uv = 0, uu = 0;
+    for (int32_t k = 0; k < kXEpsCopies; ++k) {
+        uv += a[(int64_t)k * tile_cols * 2];
+        uu += a[(int64_t)k * tile_cols * 2 + 1];
+    }
+    const double inv = 1.0 / scale[0];
+    const double duv = (double)(long long)uv * inv, duu = (double)(long long)uu * inv;
+    const double d = 1.0 - duv / sqrt(duu * vv[0]);
+    eps[(int64_t)it * B + col0 + c] = fmin(fmax(d, 0.0), 2.0);
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
+static inline size_t x_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int x_env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+struct XConfig {
+    int lob, cpl, warps, rows_per_cta;
+};
+
+static XConfig x_config(int lo_bits) {
+    XConfig c;
+    c.lob = lo_bits == 8 ? 8 : 16;
+    const int cp = x_env_int("CY2PX_CPL", 4);
+    c.cpl = cp == 2 ? 2 : (cp == 8 ? 8 : 4);
+    const int w = x_env_int("CY2PX_WARPS", 8);
+    c.warps = w >= 32 ? 32 : (w >= 16 ? 16 : 8);
+    const int r = x_env_int("CY2PX_ROWS", 0);
+    c.rows_per_cta = r > 0 ? std::max(r, c.warps) : c.warps * 8;
+    return c;
+}
+
+struct XWs {
+    size_t eps_acc, scal, part, bufA, bufB, pi_rows, total;
+    int32_t tile;      // columns per tile (multiple of the slab width)
+    uint32_t pitch;    // bytes per row of a scratch tile
+};
+
+static XWs x_ws_layout(const cy2p_plan *plan, int32_t B, int32_t iters, int want_eps, const XConfig &c) {
+    XWs w;
+    const int slab_cols = 32 * c.cpl;
+    const size_t rec = (size_t)slab_cols * 4 + (size_t)slab_cols * c.lob / 8;
+    int64_t bt = x_env_int("CY2P_TILE", 0);
+    if (bt <= 0) {
+        const size_t budget = (size_t)3 << 29;  // 1.5 GiB for the two ping-pong tiles
+        bt = (int64_t)(budget / ((size_t)plan->n * 2 * rec)) * slab_cols;
+        if (bt > 2048) bt = 2048;
+    }
+    bt = bt / slab_cols * slab_cols;
+    if (bt < slab_cols) bt = slab_cols;
+    const int64_t Bpad = ((int64_t)B + slab_cols - 1) / slab_cols * slab_cols;
+    if (bt > Bpad) bt = Bpad;
+    w.tile = (int32_t)bt;
+    w.pitch = (uint32_t)((bt / slab_cols) * rec);
+    size_t off = 0;
+    w.eps_acc = off;
+    if (want_eps) off = x_align_up(off + sizeof(unsigned long long) * 2 * (size_t)iters * (size_t)w.tile * kXEpsCopies, 256);
+    w.scal = off;
+    off = x_align_up(off + 4 * sizeof(double), 256);
+    w.part = off;
+    if (want_eps) off = x_align_up(off + sizeof(double) * (size_t)kScaleChunks * (size_t)B, 256);
+    w.bufA = off;
+    off = x_align_up(off + (size_t)plan->n * w.pitch, 256);
+    w.bufB = off;
+    off = x_align_up(off + (size_t)plan->n * w.pitch, 256);
+    w.pi_rows = off;
+    if (want_eps) off = x_align_up(off + sizeof(double) * (size_t)plan->n, 256);
+    w.total = off;
+    return w;
+}
+
+static int32_t ensure_pairsD(cy2p_plan *plan, const Pair *src, PairD **dst, cudaStream_t st) {
+    if (*dst || !src) return CY2P_OK;
+    const size_t bytes = sizeof(PairD) * (size_t)(plan->nnz ? plan->nnz : 1);
+    CY2P_CUDA(cudaMalloc((void **)dst, bytes));
+    plan->bytes_owned += bytes;
+    if (plan->nnz) {
+        count_launch();
+        widen_pairs_kernel<<<(unsigned)((plan->nnz + 255) / 256), 256, 0, st>>>(plan->nnz, src, *dst);
+    }
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+template <int LOB, int CPL, int WARPS, bool IN_F32, bool OUT_F32>
+static void x_launch_t(const XArgs &a, int32_t n, int rows_per_cta, cudaStream_t st) {
+    const int nslabs = (a.ncols + 32 * CPL - 1) / (32 * CPL);
+    const dim3 grid((unsigned)((n + rows_per_cta - 1) / rows_per_cta), (unsigned)nslabs);
+    count_launch();
+    if (a.eps_acc)
+        spmm_gather_x<LOB, CPL, WARPS, IN_F32, OUT_F32, true><<<grid, WARPS * 32, 0, st>>>(0, n, rows_per_cta, a);
+    else
+        spmm_gather_x<LOB, CPL, WARPS, IN_F32, OUT_F32, false><<<grid, WARPS * 32, 0, st>>>(0, n, rows_per_cta, a);
+}
+
+template <int LOB, int CPL>
+static void x_launch_fmt(const XArgs &a, int32_t n, const XConfig &c, bool in_f32, bool out_f32, cudaStream_t st) {
+    if (!in_f32 && !out_f32) {  // the bulk of a run: tile -> tile
+        if (c.warps == 32 && CPL < 8)
+            x_launch_t<LOB, CPL, (CPL < 8 ? 32 : 16), false, false>(a, n, c.rows_per_cta, st);
+        else if (c.warps >= 16)
+            x_launch_t<LOB, CPL, 16, false, false>(a, n, c.rows_per_cta, st);
+        else
+            x_launch_t<LOB, CPL, 8, false, false>(a, n, c.rows_per_cta, st);
+        return;
+    }
+    const int rpc = 64;
+    if (in_f32 && out_f32)
+        x_launch_t<LOB, CPL, 8, true, true>(a, n, rpc, st);
+    else if (in_f32)
+        x_launch_t<LOB, CPL, 8, true, false>(a, n, rpc, st);
+    else
+        x_launch_t<LOB, CPL, 8, false, true>(a, n, rpc, st);
+}
+
+static void x_launch(const XArgs &a, int32_t n, const XConfig &c, bool in_f32, bool out_f32, cudaStream_t st) {
+    if (c.lob == 16) {
+        if (c.cpl == 4)
+            x_launch_fmt<16, 4>(a, n, c, in_f32, out_f32, st);
+        else if (c.cpl == 8)
+            x_launch_fmt<16, 8>(a, n, c, in_f32, out_f32, st);
+        else
+            x_launch_fmt<16, 2>(a, n, c, in_f32, out_f32, st);
+    } else {
+        if (c.cpl == 4)
+            x_launch_fmt<8, 4>(a, n, c, in_f32, out_f32, st);
+        else if (c.cpl == 8)
+            x_launch_fmt<8, 8>(a, n, c, in_f32, out_f32, st);
+        else
+            x_launch_fmt<8, 2>(a, n, c, in_f32, out_f32, st);
+    }
+}
+
+}  // namespace cy2p
+
+using namespace cy2p;
+
+extern "C" {
+
+size_t cy2p_propagate_x_ws_bytes(const cy2p_plan *plan, int32_t B, int32_t iters, int32_t want_eps, int32_t tail_bits) {
+    if (!plan || B < 1 || iters < 0) return 0;
+    return x_ws_layout(plan, B, iters, want_eps, x_config(tail_bits)).total;
+}
+
+int32_t cy2p_propagate_x_column_tile(const cy2p_plan *plan, int32_t B, int32_t tail_bits) {
+    if (!plan || B < 1) return 0;
+    return x_ws_layout(plan, B, 0, 0, x_config(tail_bits)).tile;
+}
+
+int32_t cy2p_propagate_x(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t iters, const double *d_stationary,
+                         float *d_Xfinal, double *d_Xfinal64, double *d_eps, int32_t tail_bits, void *d_ws,
+                         size_t ws_bytes, void *stream) {
+    CY2P_REQUIRE(plan && d_X0, "null plan / X0");
+    CY2P_REQUIRE(B >= 1 && iters >= 0, "B >= 1 and iters >= 0 required");
+    CY2P_REQUIRE(tail_bits == 16 || tail_bits == 8, "tail_bits must be 16 (f48) or 8 (f40)");
+    CY2P_REQUIRE(!d_eps || d_stationary, "eps requested without a stationary vector");
+    CY2P_REQUIRE(d_Xfinal || d_Xfinal64, "nothing to write: both final outputs are null");
+    const XConfig c = x_config(tail_bits);
+    const XWs w = x_ws_layout(plan, B, iters, d_eps != nullptr, c);
+    if (!d_ws || ws_bytes < w.total || ((uintptr_t)d_ws & 255)) {
+        set_error("work space too small or misaligned: need %zu bytes, 256-byte aligned", w.total);
+        return CY2P_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CY2P_CUDA(cudaSetDevice(plan->device));
+    const int32_t n = plan->n;
+    char *ws = (char *)d_ws;
+    if (iters == 0) {
+        if (d_Xfinal && d_Xfinal != d_X0)
+            CY2P_CUDA(cudaMemcpyAsync(d_Xfinal, d_X0, sizeof(float) * (size_t)n * B, cudaMemcpyDeviceToDevice, st));
+        CY2P_REQUIRE(!d_Xfinal64, "iters == 0 with a float64 output is not supported");
+        return CY2P_OK;
+    }
+    // locality ordering: worth building when the work amortises the one-off host pass (same rule as cy2p_propagate)
+    if (plan->reorder_state == 0 && (int64_t)B * iters >= 4096 && B >= 32) {
+        const int32_t rc = ensure_reordered(plan, st);
+        if (rc != CY2P_OK) return rc;
+    }
+    const bool reord = plan->reorder_state == 1;
+    int32_t rc;
+    if (reord) {
+        if ((rc = ensure_pairsD(plan, plan->d_r_pairs_pp, &plan->d_r_pairsD_pp, st)) != CY2P_OK) return rc;
+        if ((rc = ensure_pairsD(plan, plan->d_r_pairs_op, &plan->d_r_pairsD_op, st)) != CY2P_OK) return rc;
+    } else {
+        if ((rc = ensure_pairsD(plan, plan->d_t_pairs, &plan->d_t_pairsD, st)) != CY2P_OK) return rc;
+    }
+    unsigned long long *eps_acc = (unsigned long long *)(ws + w.eps_acc);
+    double *scal = (double *)(ws + w.scal);  // [0] fixed-point scale, [1] |stationary|^2
+    double *pi_rows = nullptr;
+    if (d_eps) {
+        pi_rows = (double *)(ws + w.pi_rows);
+        double *part = (double *)(ws + w.part);
+        count_launch(3);
+        x_colsum_kernel<<<dim3((unsigned)((B + 255) / 256), kScaleChunks), 256, 0, st>>>(n, B, d_X0, part);
+        eps_scale_kernel<<<1, 1024, 0, st>>>(n, B, part, d_stationary, scal, scal + 1);
+        x_pi_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, d_stationary, reord ? plan->d_order : nullptr, pi_rows);
+    }
+    const bool wide_all = (B % 4 == 0) && (((uintptr_t)d_X0 & 15) == 0) && (!d_Xfinal || ((uintptr_t)d_Xfinal & 15) == 0);
+    unsigned char *bufA = (unsigned char *)(ws + w.bufA), *bufB = (unsigned char *)(ws + w.bufB);
+    for (int32_t c0 = 0; c0 < B; c0 += w.tile) {
+        const int32_t nc = (B - c0 < w.tile) ? B - c0 : w.tile;
+        if (d_eps)
+            CY2P_CUDA(cudaMemsetAsync(eps_acc, 0, sizeof(unsigned long long) * 2 * (size_t)iters * (size_t)nc * kXEpsCopies, st));
+        unsigned char *src = nullptr;
+        for (int32_t it = 0; it < iters; ++it) {
+            const bool first = it == 0, last = it + 1 == iters;
+            XArgs a;
+            a.indptr = reord ? plan->d_r_indptr : plan->d_t_indptr;
+            a.pairs = reord ? (first ? plan->d_r_pairsD_op : plan->d_r_pairsD_pp) : plan->d_t_pairsD;
+            a.dest_ids = reord ? plan->d_order : nullptr;
+            a.out_orig = reord ? 1 : 0;
+            a.xin = src;
+            a.pitch_in = w.pitch;
+            a.fin = d_X0 + c0;
+            a.ld_in = (uint32_t)B;
+            unsigned char *dst = (src == bufA) ? bufB : bufA;
+            a.xout = dst;
+            a.pitch_out = w.pitch;
+            a.fout = d_Xfinal ? d_Xfinal + c0 : nullptr;
+            a.dout = d_Xfinal64 ? d_Xfinal64 + c0 : nullptr;
+            a.ld_out = (uint32_t)B;
+            a.ncols = nc;
+            a.wide_io = (wide_all && nc % c.cpl == 0 && c0 % 4 == 0) ? 1 : 0;
+            a.pi_rows = pi_rows;
+            a.eps_acc = d_eps ? eps_acc + 2 * (size_t)it * (size_t)nc * kXEpsCopies : nullptr;
+            a.eps_scale = scal;
+            x_launch(a, n, c, first, last, st);
+            src = dst;
+        }
+        if (d_eps) {
+            const int64_t cnt = (int64_t)iters * nc;
+            count_launch();
+            x_eps_finalize<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(iters, nc, c0, B, eps_acc, scal, scal + 1, d_eps);
+        }
+    }
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
+}  // extern "C"

@@ -118,26 +118,39 @@ def iterate_state_probability(adata, matrix_key="T_forward", init=None, stationa
     return state_history, state_history_max_iter, convergence_check
 
 
+PRECISIONS = ("f48", "f40", "fp64", "fp32")
+
+
 def propagate_batch(adata_or_T, X0, iters, stationary=None, matrix_key="T_forward", tol=1e-5, return_device=False,
-                    precision="fp32"):
+                    precision="f48", out_dtype=None):
     """Batched form of the same simulation (BASELINE configs 2/4): B start distributions at once.
 
-    X0: [n, B] float32 (numpy or cuda tensor), cell-major. Returns dict with ``final`` [n, B] and, when
+    X0: [n, B] (numpy or cuda tensor), cell-major. Returns dict with ``final`` [n, B] and, when
     ``stationary`` is given, ``eps`` [iters, B] float64 and ``convergence`` [B] (the per-start cut of
     reference sampling.py:48-57). The full [iters, n, B] history is not materialised (1.6 PB at config 2).
-    ``precision``: "fp32" (default, the throughput path) or "fp64" (float64 iterate: tracks the reference's
-    float64 arithmetic over thousands of iterations at twice the memory traffic)."""
+
+    ``precision`` names the iterate the device carries between updates (the reference's is float64,
+    sampling.py:33; products and row sums are float64 in every mode but "fp32"):
+      "f48"  (default) truncated float64, 36 mantissa bits, 6 bytes: within 1e-9 relative L1 of the reference
+             after 2,000 updates; X0 is taken as float32, ``final`` is float32 (``out_dtype=torch.float64``: float64)
+      "f40"  truncated float64, 28 mantissa bits, 5 bytes: ~1e-10 relative L1 per update (2e-7 after 2,000)
+      "fp64" float64 iterate, 8 bytes (X0 / final float64)
+      "fp32" float32 iterate and arithmetic: the fastest, but it leaves the north_star's 1e-6 relative-L1 bar after
+             ~60-100 updates (2e-8 per update, DESIGN.md "precision"); kept for short runs and as a measurement"""
     import torch
 
-    if precision not in ("fp32", "fp64"):
-        raise ValueError("precision must be 'fp32' or 'fp64'")
-    tdt = torch_dtype(precision)
-
+    if precision not in PRECISIONS:
+        raise ValueError("precision must be one of %s" % (PRECISIONS,))
     T = adata_or_T.obsp[matrix_key] if hasattr(adata_or_T, "obsp") else adata_or_T
     plan = get_plan(T)
-    x0 = _lib.to_device(X0, tdt, plan.device)
-    out = _lib.propagate(plan, x0, int(iters), stationary=stationary, want_final=True, history_stride=0,
-                         want_eps=stationary is not None)
+    if precision in ("f48", "f40"):
+        x0 = _lib.to_device(X0, torch.float32, plan.device)
+        out = _lib.propagate_x(plan, x0, int(iters), stationary=stationary, tail_bits=16 if precision == "f48" else 8,
+                               want_eps=stationary is not None, out_dtype=out_dtype)
+    else:
+        x0 = _lib.to_device(X0, torch_dtype(precision), plan.device)
+        out = _lib.propagate(plan, x0, int(iters), stationary=stationary, want_final=True, history_stride=0,
+                             want_eps=stationary is not None)
     conv_d = batch_convergence_device(out["eps"], tol, int(iters)) if out["eps"] is not None else None
     fin, eps, conv = _lib.to_host_many([None if return_device else out["final"], out["eps"], conv_d])
     res = {"final": out["final"] if return_device else fin}

@@ -93,6 +93,23 @@ int32_t cy2p_propagate_f64(cy2p_plan *plan, const double *d_X0, int32_t B, int32
                            const double *d_stationary, double *d_Xfinal, double *d_history,
                            int32_t history_stride, double *d_eps, void *d_ws, size_t ws_bytes, void *stream);
 
+/* Extended-precision iterate for the BATCHED case (the default of cy2path_b200.sampling.propagate_batch): same
+ * update, but the products and row sums are float64 (like scipy's upcast product at sampling.py:40-42) and the
+ * iterate between updates is a truncated float64 — sign, 11-bit exponent and 20 + tail_bits mantissa bits, i.e.
+ * 6 bytes per element for tail_bits = 16 ("f48"), 5 for tail_bits = 8 ("f40") — in a tiled work-space layout
+ * (csrc/propagate_x.cu). A float32 iterate leaves the reference's float64 iterate by a relative L1 distance of
+ * ~2e-8 per update (4e-5 after 2,000); f48 stays below 1e-9, f40 below 2e-7 (tools/precision_lab.py).
+ *   d_X0        [n][B] float32 (exact in the wider format)
+ *   d_Xfinal    [n][B] float32 or NULL;  d_Xfinal64 [n][B] float64 or NULL (at least one)
+ *   d_eps       NULL or [iters][B] float64, BIT-REPRODUCIBLE: float64 partial sums per thread in a fixed order,
+ *               64-bit fixed-point integer atomics across threads (integer addition is associative)
+ *   want_eps    for the work-space size: 1 if d_eps will be non-NULL */
+size_t cy2p_propagate_x_ws_bytes(const cy2p_plan *plan, int32_t B, int32_t iters, int32_t want_eps, int32_t tail_bits);
+int32_t cy2p_propagate_x_column_tile(const cy2p_plan *plan, int32_t B, int32_t tail_bits);
+int32_t cy2p_propagate_x(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t iters,
+                         const double *d_stationary, float *d_Xfinal, double *d_Xfinal64, double *d_eps,
+                         int32_t tail_bits, void *d_ws, size_t ws_bytes, void *stream);
+
 /* Row-partitioned variant (BASELINE config 5): computes only destination rows [row_begin,row_end)
  * of one update, Y[row_begin:row_end, :] = (X . T)[row_begin:row_end, :], reading the whole X.
  * The caller (cy2path_b200/dist.py) all-gathers the slices between iterations. */
