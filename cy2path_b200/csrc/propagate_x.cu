@@ -161,7 +161,7 @@ __device__ __forceinline__ void x_round(double y, uint32_t &hi, uint32_t &tail, 
     yr = mk_double(low & ~((1u << drop) - 1u), hi);
 }
 
-template <int LOB, int CPL, int WARPS, bool IN_F32, bool OUT_F32, bool EPS>
+template <int LOB, int CPL, int WARPS, int U, bool IN_F32, bool OUT_F32, bool EPS>
 __device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int32_t row1, int slab, int copy_sel,
                                                unsigned long long (*s_acc)[CPL][32], unsigned *s_done) {
     using F = XFmt<LOB, CPL>;
@@ -184,45 +184,69 @@ __device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int
         const float *fin = a.fin + col;
         const bool wide = a.wide_io != 0;
         const uint32_t pitch_in = a.pitch_in;
-        for (int32_t r = row0 + warp; r < row1; r += WARPS) {
-            int32_t p = __ldg(a.indptr + r);
-            const int32_t end = __ldg(a.indptr + r + 1);
+        // Software pipeline over the warp's stream of entries: the (source, value) entries of group g+1 — the next U
+        // entries of this row or the first U of the warp's NEXT row, whose row pointers were fetched one row ahead —
+        // are requested before the gathers of group g are consumed, so an update costs one exposed L2 round trip per
+        // group instead of two dependent ones (entries, then rows); ncu of the unpipelined loop: 74% of the issue
+        // latency was the long scoreboard at 31% occupancy, nothing saturated (profiles/README_r02.md).
+        auto load_entries = [&](uint4 *q, int32_t p, int32_t end) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                q[u] = (p + u < end) ? __ldg(reinterpret_cast<const uint4 *>(pairs + p + u)) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        int32_t r = row0 + warp;
+        int32_t p = 0, end = 0;
+        if (r < row1) p = __ldg(a.indptr + r), end = __ldg(a.indptr + r + 1);
+        uint4 q[U];
+        load_entries(q, p, end);
+        for (; r < row1; r += WARPS) {
+            const int32_t rn = r + WARPS;
+            int32_t pn = 0, endn = 0;
+            if (rn < row1) pn = __ldg(a.indptr + rn), endn = __ldg(a.indptr + rn + 1);
             const double pi = EPS ? __ldg(a.pi_rows + r) : 0.0;
             const int32_t orow = (OUT_F32 && a.out_orig) ? __ldg(a.dest_ids + r) : r;
             double acc[CPL];
 #pragma unroll
             for (int k = 0; k < CPL; ++k) acc[k] = 0.0;
-            constexpr int U = CPL >= 8 ? 2 : 4;  // row gathers in flight per warp
-            for (; p + U - 1 < end; p += U) {
-                uint4 q[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) q[u] = __ldg(reinterpret_cast<const uint4 *>(pairs + p + u));
+            do {  // an empty row runs one group of padding entries (value 0, loads skipped)
+                uint4 qn[U];
                 if (IN_F32) {
                     FLoad<CPL> x[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) x[u].issue(fin + (uint64_t)q[u].x * a.ld_in, nvalid, wide);
+                    for (int u = 0; u < U; ++u) {
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) x[u].x[k] = 0.f;
+                        if (p + u < end) x[u].issue(fin + (uint64_t)q[u].x * a.ld_in, nvalid, wide);
+                    }
+                    p += U;
+                    if (p < end)
+                        load_entries(qn, p, end);
+                    else
+                        load_entries(qn, pn, endn);
 #pragma unroll
                     for (int u = 0; u < U; ++u) x[u].fma(mk_double(q[u].z, q[u].w), acc);
                 } else {
                     XLoad<LOB, CPL> x[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) x[u].issue(row_ptr(xhi, q[u].x, pitch_in), row_ptr(xlo, q[u].x, pitch_in));
+                    for (int u = 0; u < U; ++u) {
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) x[u].h[k] = 0u;
+#pragma unroll
+                        for (int k = 0; k < XLoad<LOB, CPL>::kLoWords; ++k) x[u].l[k] = 0u;
+                        if (p + u < end) x[u].issue(row_ptr(xhi, q[u].x, pitch_in), row_ptr(xlo, q[u].x, pitch_in));
+                    }
+                    p += U;
+                    if (p < end)
+                        load_entries(qn, p, end);
+                    else
+                        load_entries(qn, pn, endn);
 #pragma unroll
                     for (int u = 0; u < U; ++u) x[u].fma(mk_double(q[u].z, q[u].w), acc);
                 }
-            }
-            for (; p < end; ++p) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(pairs + p));
-                if (IN_F32) {
-                    FLoad<CPL> x;
-                    x.issue(fin + (uint64_t)q.x * a.ld_in, nvalid, wide);
-                    x.fma(mk_double(q.z, q.w), acc);
-                } else {
-                    XLoad<LOB, CPL> x;
-                    x.issue(row_ptr(xhi, q.x, pitch_in), row_ptr(xlo, q.x, pitch_in));
-                    x.fma(mk_double(q.z, q.w), acc);
-                }
-            }
+#pragma unroll
+                for (int u = 0; u < U; ++u) q[u] = qn[u];
+            } while (p < end);
+            p = pn, end = endn;
             // ---- store the row in the stored format (or as float32 / float64 on the last update)
             uint32_t hi[CPL], tl[CPL];
             double yr[CPL];
@@ -311,21 +335,15 @@ __device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int
     }
 }
 
-// resident CTAs per SM the register budget is compiled for (8 columns per lane keep 16 float64 accumulators and, with
-// eps, 32 registers of partial sums: 128 registers, 16 warps per SM)
-template <int WARPS, int CPL>
-struct XOcc {
-    static constexpr int kMinBlocks = CPL >= 8 ? (WARPS <= 8 ? 2 : 1) : (WARPS <= 8 ? 3 : (WARPS <= 16 ? 2 : 1));
-};
-
-template <int LOB, int CPL, int WARPS, bool IN_F32, bool OUT_F32, bool EPS>
-__global__ void __launch_bounds__(WARPS * 32, XOcc<WARPS, CPL>::kMinBlocks)
+// MINB = resident CTAs per SM the register budget is compiled for, U = row gathers in flight per warp
+template <int LOB, int CPL, int WARPS, int MINB, int U, bool IN_F32, bool OUT_F32, bool EPS>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 spmm_gather_x(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, XArgs a) {
     __shared__ unsigned long long s_acc[2][CPL][32];
     __shared__ unsigned s_done;
     const int32_t row0 = row_begin + blockIdx.x * rows_per_cta;
-    gather_block_x<LOB, CPL, WARPS, IN_F32, OUT_F32, EPS>(a, row0, min(row0 + rows_per_cta, row_end), blockIdx.y,
-                                                          blockIdx.x % kXEpsCopies, s_acc, &s_done);
+    gather_block_x<LOB, CPL, WARPS, U, IN_F32, OUT_F32, EPS>(a, row0, min(row0 + rows_per_cta, row_end), blockIdx.y,
+                                                             blockIdx.x % kXEpsCopies, s_acc, &s_done);
 }
 
 // ---- small kernels ----------------------------------------------------------------------------------------------
@@ -425,16 +443,17 @@ static int x_env_int(const char *name, int dflt) {
 }
 
 struct XConfig {
-    int lob, cpl, warps, rows_per_cta;
+    int lob, cpl, warps, rows_per_cta, minb, u;
 };
 
 static XConfig x_config(int lo_bits) {
     XConfig c;
     c.lob = lo_bits == 8 ? 8 : 16;
-    const int cp = x_env_int("CY2PX_CPL", 4);
-    c.cpl = cp == 2 ? 2 : (cp == 8 ? 8 : 4);
+    c.cpl = x_env_int("CY2PX_CPL", 8) == 4 ? 4 : 8;
+    c.minb = x_env_int("CY2PX_MINB", 2);
+    c.u = x_env_int("CY2PX_U", 4) == 2 ? 2 : 4;
     const int w = x_env_int("CY2PX_WARPS", 8);
-    c.warps = w >= 32 ? 32 : (w >= 16 ? 16 : 8);
+    c.warps = w >= 16 ? 16 : 8;
     const int r = x_env_int("CY2PX_ROWS", 0);
     c.rows_per_cta = r > 0 ? std::max(r, c.warps) : c.warps * 8;
     return c;
@@ -492,52 +511,61 @@ static int32_t ensure_pairsD(cy2p_plan *plan, const Pair *src, PairD **dst, cuda
     return CY2P_OK;
 }
 
-template <int LOB, int CPL, int WARPS, bool IN_F32, bool OUT_F32>
+template <int LOB, int CPL, int WARPS, int MINB, int U, bool IN_F32, bool OUT_F32>
 static void x_launch_t(const XArgs &a, int32_t n, int rows_per_cta, cudaStream_t st) {
     const int nslabs = (a.ncols + 32 * CPL - 1) / (32 * CPL);
     const dim3 grid((unsigned)((n + rows_per_cta - 1) / rows_per_cta), (unsigned)nslabs);
     count_launch();
     if (a.eps_acc)
-        spmm_gather_x<LOB, CPL, WARPS, IN_F32, OUT_F32, true><<<grid, WARPS * 32, 0, st>>>(0, n, rows_per_cta, a);
+        spmm_gather_x<LOB, CPL, WARPS, MINB, U, IN_F32, OUT_F32, true><<<grid, WARPS * 32, 0, st>>>(0, n, rows_per_cta, a);
     else
-        spmm_gather_x<LOB, CPL, WARPS, IN_F32, OUT_F32, false><<<grid, WARPS * 32, 0, st>>>(0, n, rows_per_cta, a);
+        spmm_gather_x<LOB, CPL, WARPS, MINB, U, IN_F32, OUT_F32, false><<<grid, WARPS * 32, 0, st>>>(0, n, rows_per_cta, a);
+}
+
+// tile -> tile updates (the bulk of a run): the tuning knobs select the instantiation. Measured on B200 at config 2
+// (profiles/k1x_sweep2_r02.jsonl): the update runs against the L2 -> SM bandwidth cap, and what decides how close it
+// gets is the number of gathered bytes a SM has in flight (24 KB: 4.5 ms per update, 49 KB: 3.1-3.8, 73 KB: 2.9-3.0,
+// 98 KB: 2.7) — in-flight bytes are registers, so the best shape is few fat warps: 8 columns per lane, 4 row gathers
+// in flight, 128 registers, 16 warps per SM. Shapes that spill (64-register budgets) lose 15-30%.
+template <int LOB, int CPL, int U>
+static void x_launch_hot(const XArgs &a, int32_t n, const XConfig &c, cudaStream_t st) {
+    if (c.warps == 16)
+        x_launch_t<LOB, CPL, 16, 1, U, false, false>(a, n, c.rows_per_cta, st);
+    else if (c.minb == 3)
+        x_launch_t<LOB, CPL, 8, 3, U, false, false>(a, n, c.rows_per_cta, st);
+    else
+        x_launch_t<LOB, CPL, 8, 2, U, false, false>(a, n, c.rows_per_cta, st);
 }
 
 template <int LOB, int CPL>
 static void x_launch_fmt(const XArgs &a, int32_t n, const XConfig &c, bool in_f32, bool out_f32, cudaStream_t st) {
-    if (!in_f32 && !out_f32) {  // the bulk of a run: tile -> tile
-        if (c.warps == 32 && CPL < 8)
-            x_launch_t<LOB, CPL, (CPL < 8 ? 32 : 16), false, false>(a, n, c.rows_per_cta, st);
-        else if (c.warps >= 16)
-            x_launch_t<LOB, CPL, 16, false, false>(a, n, c.rows_per_cta, st);
+    if (!in_f32 && !out_f32) {
+        if (c.u == 2)
+            x_launch_hot<LOB, CPL, 2>(a, n, c, st);
         else
-            x_launch_t<LOB, CPL, 8, false, false>(a, n, c.rows_per_cta, st);
+            x_launch_hot<LOB, CPL, 4>(a, n, c, st);
         return;
     }
-    const int rpc = 64;
+    const int rpc = 64;  // first / last update of a run: float32 rows in or out
     if (in_f32 && out_f32)
-        x_launch_t<LOB, CPL, 8, true, true>(a, n, rpc, st);
+        x_launch_t<LOB, CPL, 8, 2, 2, true, true>(a, n, rpc, st);
     else if (in_f32)
-        x_launch_t<LOB, CPL, 8, true, false>(a, n, rpc, st);
+        x_launch_t<LOB, CPL, 8, 2, 2, true, false>(a, n, rpc, st);
     else
-        x_launch_t<LOB, CPL, 8, false, true>(a, n, rpc, st);
+        x_launch_t<LOB, CPL, 8, 2, 2, false, true>(a, n, rpc, st);
 }
 
 static void x_launch(const XArgs &a, int32_t n, const XConfig &c, bool in_f32, bool out_f32, cudaStream_t st) {
     if (c.lob == 16) {
-        if (c.cpl == 4)
-            x_launch_fmt<16, 4>(a, n, c, in_f32, out_f32, st);
-        else if (c.cpl == 8)
+        if (c.cpl == 8)
             x_launch_fmt<16, 8>(a, n, c, in_f32, out_f32, st);
         else
-            x_launch_fmt<16, 2>(a, n, c, in_f32, out_f32, st);
+            x_launch_fmt<16, 4>(a, n, c, in_f32, out_f32, st);
     } else {
-        if (c.cpl == 4)
-            x_launch_fmt<8, 4>(a, n, c, in_f32, out_f32, st);
-        else if (c.cpl == 8)
+        if (c.cpl == 8)
             x_launch_fmt<8, 8>(a, n, c, in_f32, out_f32, st);
         else
-            x_launch_fmt<8, 2>(a, n, c, in_f32, out_f32, st);
+            x_launch_fmt<8, 4>(a, n, c, in_f32, out_f32, st);
     }
 }
 

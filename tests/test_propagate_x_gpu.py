@@ -61,8 +61,8 @@ def test_small_cases_match_oracle(B, iters, tail):
     assert _rel_l1_cols(g64, ref) <= (iters * 2e-11 if tail == 16 else iters * 5e-9)
 
 
-@pytest.mark.parametrize("cpl,warps", [(2, 8), (4, 16), (4, 32), (8, 8), (8, 16)])
-def test_kernel_shape_variants_agree(monkeypatch, cpl, warps):
+@pytest.mark.parametrize("cpl,warps,minb,u", [(4, 8, 2, 2), (4, 8, 3, 4), (4, 16, 1, 4), (8, 8, 3, 2), (8, 16, 1, 2)])
+def test_kernel_shape_variants_agree(monkeypatch, cpl, warps, minb, u):
     """The tuning variants (columns per lane, warps per CTA) walk the same rows in the same order: identical bits."""
     import torch
 
@@ -77,6 +77,8 @@ def test_kernel_shape_variants_agree(monkeypatch, cpl, warps):
     base = _lib.propagate_x(plan, X0, 30, stationary=stat, want_eps=True)
     monkeypatch.setenv("CY2PX_CPL", str(cpl))
     monkeypatch.setenv("CY2PX_WARPS", str(warps))
+    monkeypatch.setenv("CY2PX_MINB", str(minb))
+    monkeypatch.setenv("CY2PX_U", str(u))
     for tail in (16, 8):
         ref = base if tail == 16 else None
         got = _lib.propagate_x(plan, X0, 30, stationary=stat, want_eps=True, tail_bits=tail)

@@ -12,29 +12,25 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 # name -> (kind, tail_bits, env)
+def _x(tail, **env):
+    return ("x", tail, {"CY2PX_" + k.upper(): str(v) for k, v in env.items()})
+
+
 CONFIGS = {
-    "f48_c4_w8": ("x", 16, {}),
-    "f48_c4_w16": ("x", 16, {"CY2PX_WARPS": "16"}),
-    "f48_c4_w32": ("x", 16, {"CY2PX_WARPS": "32"}),
-    "f48_c4_w16_r64": ("x", 16, {"CY2PX_WARPS": "16", "CY2PX_ROWS": "64"}),
-    "f48_c4_w32_r128": ("x", 16, {"CY2PX_WARPS": "32", "CY2PX_ROWS": "128"}),
-    "f48_c4_w8_r32": ("x", 16, {"CY2PX_ROWS": "32"}),
-    "f48_c4_w8_r128": ("x", 16, {"CY2PX_ROWS": "128"}),
-    "f48_c8_w8": ("x", 16, {"CY2PX_CPL": "8"}),
-    "f48_c8_w16": ("x", 16, {"CY2PX_CPL": "8", "CY2PX_WARPS": "16"}),
-    "f48_c2_w8": ("x", 16, {"CY2PX_CPL": "2"}),
-    "f48_c2_w16": ("x", 16, {"CY2PX_CPL": "2", "CY2PX_WARPS": "16"}),
-    "f48_c2_w32": ("x", 16, {"CY2PX_CPL": "2", "CY2PX_WARPS": "32"}),
-    "f48_c4_w8_t1024": ("x", 16, {"CY2P_TILE": "1024"}),
-    "f48_c4_w8_t512": ("x", 16, {"CY2P_TILE": "512"}),
-    "f48_c4_w8_t128": ("x", 16, {"CY2P_TILE": "128"}),
-    "f40_c4_w8": ("x", 8, {}),
-    "f40_c4_w16": ("x", 8, {"CY2PX_WARPS": "16"}),
-    "f40_c8_w8": ("x", 8, {"CY2PX_CPL": "8"}),
-    "f40_c2_w16": ("x", 8, {"CY2PX_CPL": "2", "CY2PX_WARPS": "16"}),
     "fp32": ("f32", 0, {}),
     "fp64": ("f64", 0, {}),
 }
+for _tail, _nm in ((16, "f48"), (8, "f40")):
+    for _cpl in (4, 8):
+        for _w, _mb in ((8, 2), (8, 3), (16, 1)):
+            for _u in (2, 4):
+                CONFIGS["%s_c%d_w%d_m%d_u%d" % (_nm, _cpl, _w, _mb, _u)] = _x(_tail, cpl=_cpl, warps=_w, minb=_mb, u=_u)
+CONFIGS["f48_default"] = ("x", 16, {})
+CONFIGS["f40_default"] = ("x", 8, {})
+for _t in (128, 512, 1024):
+    CONFIGS["f48_default_t%d" % _t] = ("x", 16, {"CY2P_TILE": str(_t)})
+for _r in (32, 128, 256):
+    CONFIGS["f48_default_r%d" % _r] = ("x", 16, {"CY2PX_ROWS": str(_r)})
 
 
 def main():
@@ -62,7 +58,7 @@ def main():
     out = open(a.out, "a") if a.out else None
     for name in names:
         kind, tail, env = CONFIGS[name]
-        saved = {k: os.environ.get(k) for k in ("CY2PX_CPL", "CY2PX_WARPS", "CY2PX_ROWS", "CY2P_TILE")}
+        saved = {k: os.environ.get(k) for k in ("CY2PX_CPL", "CY2PX_WARPS", "CY2PX_ROWS", "CY2P_TILE", "CY2PX_MINB", "CY2PX_U")}
         for k in saved:
             os.environ.pop(k, None)
         os.environ.update(env)
