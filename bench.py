@@ -8,9 +8,18 @@ A "step" is one pass of the hot path over one batch of synthetic input of BASELI
 metric = MSM simulation cell-iterations/s = n*B*iters / step time (the chain sampling is inside the
 timed step; its own rate is reported under "detail").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision f48|f40|fp64|fp32] [--no-extras]
 N > 1 is launched by torchrun (one rank per GPU); every rank runs the same per-GPU workload on its own
 start distributions / chains (T replicated, no data-path collective) => weak scaling.
+
+The batched propagation runs with the extended-precision iterate ("f48", the default of propagate_batch): the path
+that holds the north_star's 1e-6 relative-L1 bar at 2,000 iterations (tests/test_propagate_x_gpu.py). The float32
+iterate's rate is reported under detail.fp32_outside_tolerance, labelled as such.
+
+Besides the headline (config 2) the same run reports, under "detail" (skipped with --no-extras):
+  config3_fhmm     factorial latent model, S=10 L=4 N=50,000 I=500: ms per epoch (loss + analytic gradients + RMSprop)
+  config4_strong   250,000-cell TPM, 4,096 starts split 4,096/N per GPU, a 100-iteration slice of the 1,000
+  config5_rowpart  1,000,000-cell TPM row-partitioned over the N GPUs, B = 1 and B = 256, fused update + halo push
 """
 import argparse
 import json
@@ -45,6 +54,7 @@ def parse():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip detail.config3_fhmm / config4_strong / config5_rowpart")
     ap.add_argument("--precision", default="f48", choices=["f48", "f40", "fp64", "fp32"],
                     help="iterate of the batched propagation (f48 = default of propagate_batch: inside the "
                          "north_star tolerance at 2,000 iterations; fp32 is outside it beyond ~60)")
@@ -128,7 +138,7 @@ def _cpu_worker(args):
     return float(X.sum())
 
 
-def cpu_reference_rate(inp, w, cores, b_per_core, iters, pool=None):
+def cpu_reference_rate(inp, w, cores, b_per_core, iters, pool=None, worker=None):
     """cell-iterations/s of the oracle port (same scipy code path the reference executes) on `cores` processes."""
     import multiprocessing as mp
 
@@ -141,11 +151,12 @@ def cpu_reference_rate(inp, w, cores, b_per_core, iters, pool=None):
     own = pool is None
     if own:
         pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+    worker = worker or _cpu_worker
     t0 = time.perf_counter()
     if pool is None:
-        _cpu_worker(jobs[0])
+        worker(jobs[0])
     else:
-        pool.map(_cpu_worker, jobs)
+        pool.map(worker, jobs)
     dt = time.perf_counter() - t0
     if own and pool is not None:
         pool.close()
@@ -167,7 +178,45 @@ def cpu_chain_rate(inp, w, chains=2000):
     return chains * uni.shape[1] / (time.perf_counter() - t0)
 
 
+def _ref_worker(args):
+    """One worker of the reference arm proper: the UNMODIFIED reference function
+    `cy2path.sampling.iterate_state_probability` (sampling.py:29-60: scipy `x @ T` + scipy cosine per iteration, full
+    float64 history) from oracle/_ref (copied from /root/reference by __graft_entry__.build()), one call per start."""
+    indptr, indices, data, n, Xs, stat, iters = args
+    import logging
+
+    import scipy.sparse as sp
+    from threadpoolctl import threadpool_limits
+
+    os.environ["TQDM_DISABLE"] = "1"
+    from oracle import ref_shim
+
+    ref = ref_shim.load()
+    logging.disable(logging.WARNING)  # the reference logs "Max number of iterations reached" per call
+    T = sp.csr_matrix((data, indices, indptr), shape=(n, n))
+    ad = ref_shim.DuckAnnData(T)
+    acc = 0.0
+    with threadpool_limits(1):
+        for b in range(Xs.shape[0]):
+            _, hist, _ = ref.sampling.iterate_state_probability(ad, init=np.asarray(Xs[b], dtype=np.float64),
+                                                                stationary=stat, max_iter=iters)
+            acc += float(hist[-1].sum())
+    return acc
+
+
+def reference_available():
+    try:
+        from oracle import ref_shim
+
+        return ref_shim.available()
+    except Exception:
+        return False
+
+
 def run_reference(args, w):
+    """`--impl reference`: the reference's own CPU implementation of the path on all host cores, a bounded sample of
+    the arm's workload per step (one process per core over disjoint start distributions; scipy's product is
+    single-threaded). kind = "reference" when oracle/_ref holds the reference modules, else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -176,24 +225,28 @@ def run_reference(args, w):
     inp = make_inputs(w, 0, with_chains=False)
     cores = max(1, min(os.cpu_count() or 1, 64))
     b_per_core, iters = 8, 25  # bounded sample per step: cores*8 starts x 25 iterations
+    use_ref = reference_available()
+    worker = _ref_worker if use_ref else _cpu_worker
     pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
     for _ in range(args.warmup):
-        cpu_reference_rate(inp, w, cores, b_per_core, max(1, iters // 5), pool)
+        cpu_reference_rate(inp, w, cores, b_per_core, max(1, iters // 5), pool, worker)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_rate(inp, w, cores, b_per_core, iters, pool)
+        cpu_reference_rate(inp, w, cores, b_per_core, iters, pool, worker)
     dt = time.perf_counter() - t0
     if pool is not None:
         pool.close()
     value = w["n"] * b_per_core * cores * iters * args.steps / dt
-    sample = f"{cores} processes x {b_per_core} starts x {iters} iterations per step, scipy x@T + cosine"
+    sample = (f"{cores} processes x {b_per_core} starts x {iters} iterations per step, " +
+              ("cy2path.sampling.iterate_state_probability (unmodified, oracle/_ref), one call per start"
+               if use_ref else "oracle port: scipy x@T + cosine"))
     line = {
         "impl": "reference", "metric": "msm_cell_iterations_per_s", "value": value, "unit": "cell-iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(w, args, 1),
-        "cpu_baseline": {"value": value, "unit": "cell-iterations/s", "cores": cores, "kind": "port",
-                         "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "cell-iterations/s", "cores": cores,
+                         "kind": "reference" if use_ref else "port", "sample": sample},
         "e2e": {"value": value, "unit": "cell-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -208,6 +261,206 @@ def workload_config(w, args, world):
             "n": w["n"], "nnz": w["n"] * w["k"], "B_per_gpu": w["B"], "iters": w["iters"],
             "chains_per_gpu": w["chains"], "chain_len": w["max_iter"], "parallelism": f"batch-shard x{world}",
             "l2_policy": "inputs larger than L2 (X0 is %.0f MB per GPU)" % (w["n"] * w["B"] * 4 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------ extras (detail.*)
+def shared_graph(n, seed, rank, barrier, k=30):
+    """The synthetic TPM of an extra section, generated ONCE per box (rank 0) and shared through /tmp: all ranks must
+    hold the identical graph, and eight concurrent generations of a 10^6-cell graph would only fight for the host."""
+    import scipy.sparse as sp
+
+    path = f"/tmp/cy2p_bench_graph_{n}_{k}_{seed}.npz"
+    if rank == 0 and not os.path.exists(path):
+        from cy2path_b200.synth import knn_velocity_tpm
+
+        g = knn_velocity_tpm(n, k=k, seed=seed)
+        np.savez(path + ".tmp.npz", indptr=g["T"].indptr, indices=g["T"].indices, data=g["T"].data,
+                 root_cells=g["root_cells"])
+        os.replace(path + ".tmp.npz", path)
+    barrier()
+    z = np.load(path)
+    T = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+    return T, z["root_cells"]
+
+
+def _max_over_ranks(ms, dev, world):
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([float(ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def extra_config4(rank, world, dev, barrier, peak_gbs):
+    """BASELINE config 4: 250,000-cell TPM, 4,096 start distributions split 4,096 / N per GPU (STRONG scaling, T
+    replicated, no collective), extended-precision iterate + eps like the headline; a 100-iteration slice of the
+    1,000 the config names (the rate per iteration does not depend on the count)."""
+    import torch
+
+    from cy2path_b200 import _lib
+    from cy2path_b200.dist import shard_range
+    from cy2path_b200.synth import batched_starts, stationary_by_power
+
+    n, Btot, iters_named, iters = 250_000, 4096, 1000, 100
+    T, _ = shared_graph(n, 4, rank, barrier)
+    b0, b1 = shard_range(Btot, world, rank)
+    Bl = b1 - b0
+    plan = _lib.Plan(T)
+    stat = torch.from_numpy(stationary_by_power(T, 50)).to(dev)
+    X0 = torch.from_numpy(batched_starts(T, Bl, seed=4 + 1000 * rank)).to(dev)
+    _lib.propagate_x(plan, X0, 6, stationary=stat, want_eps=True)  # builds the ordering, warms up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.propagate_x(plan, X0, iters, stationary=stat, want_eps=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1), dev, world)
+    del X0, plan
+    torch.cuda.empty_cache()
+    bytes_gpu = (8 * T.nnz + 4 * (n + 1) + 8 * n * Bl) * iters
+    return {"workload": f"250,000 cells, 4,096 starts split {Bl} per GPU, {iters} of the {iters_named} iterations, f48 + eps",
+            "scaling": "strong", "collective": "none (T replicated, columns independent)", "n_gpus": world,
+            "cell_iterations_per_s": n * Btot * iters / (ms * 1e-3), "ms_per_iteration": ms / iters,
+            "hbm_roofline_frac_per_gpu": bytes_gpu / (ms * 1e-3) / 1e9 / peak_gbs}
+
+
+def extra_config3(rank, dev, T, plan):
+    """BASELINE config 3: FHMM, S = 10, L = 4, N = 50,000 cells, I = 500 history rows, restricted emissions, default
+    weights; one epoch = cy2p_fhmm_loss_grad (forward + loss terms + analytic gradients) + torch's RMSprop step.
+    The CPU figure beside it is the oracle's eager-torch restatement of the reference's epoch (trainer.py:134-201:
+    forward_model + loss + autograd backward) at the largest shape that fits the host in seconds."""
+    import torch
+
+    from cy2path_b200 import _lib, models
+
+    if rank != 0:
+        return None
+    N, I, S, L = T.shape[0], 500, 10, 4
+    from cy2path_b200.synth import knn_velocity_tpm  # noqa: F401  (inputs come from the headline's graph)
+
+    x0 = torch.full((N,), 1.0 / N, dtype=torch.float64, device=dev)
+    D = _lib.propagate(plan, x0, I, history_stride=1, want_final=False)["history"].float().contiguous()
+    torch.manual_seed(3)
+    m = models.FHMM(S, L, N, I, restricted=True, use_gpu=True)
+    params = [p.data for p in m.parameters()]
+    w = (1.0, 0.1, 0.1, 0.05)
+    _, _, bufs = _lib.fhmm_loss_grad(plan, *params, D, True, w)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    e0.record()
+    for _ in range(reps):
+        _lib.fhmm_loss_grad(plan, *params, D, True, w, out=bufs)
+    e1.record()
+    torch.cuda.synchronize()
+    lg_ms = e0.elapsed_time(e1) / reps
+    m.train(D, TPM=T, num_epochs=5)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    epochs = 100
+    m.train(D, TPM=T, num_epochs=epochs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {"workload": "FHMM S=10 L=4 N=50,000 I=500 restricted, default loss weights, RMSprop",
+           "loss_grad_ms": lg_ms, "epoch_ms": dt / epochs * 1e3, "epochs_per_s": epochs / dt,
+           "D_bytes": N * I * 4, "D_pass_GBps_over_whole_call": N * I * 4 / (lg_ms * 1e-3) / 1e9,
+           "loss_first": float(m.loss_values[0]), "loss_last": float(m.loss_values[-1])}
+    try:  # CPU baseline (oracle = test infrastructure; allowed here as the cpu_baseline leg only)
+        import scipy.sparse as sp
+
+        from cy2path_b200.synth import knn_velocity_tpm
+        from oracle import fhmm as ofhmm
+
+        Nr, Ir = 3696, 430
+        gr = knn_velocity_tpm(Nr, seed=3)
+        coo = sp.coo_matrix(gr["T"])
+        Tt = torch.sparse_coo_tensor(np.vstack([coo.row, coo.col]), coo.data.astype(np.float32), (Nr, Nr)).coalesce()
+        Dr = torch.rand(Ir, Nr)
+        Dr /= Dr.sum(1, keepdim=True)
+        torch.manual_seed(3)
+        th = [torch.randn(S, L, requires_grad=True), torch.randn(L, requires_grad=True),
+              torch.randn(S, 1, Nr, requires_grad=True), torch.randn(L, S, S, requires_grad=True)]
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            for t in th:
+                t.grad = None
+            ofhmm.loss_terms(*th, Dr, Tt, weights=w)["loss"].backward()
+        cpu_s = (time.perf_counter() - t0) / reps
+        out["cpu_baseline"] = {"epoch_ms": cpu_s * 1e3, "kind": "port", "cores": torch.get_num_threads(),
+                               "sample": f"oracle eager torch epoch (forward + loss + autograd) at N={Nr}, I={Ir}",
+                               "cell_iterations_per_s": Nr * Ir / cpu_s}
+        out["cell_iterations_per_s"] = N * I * epochs / dt
+    except Exception as e:  # pragma: no cover
+        out["cpu_baseline"] = {"error": repr(e)[:200]}
+    return out
+
+
+def extra_config5(rank, world, dev, barrier):
+    """BASELINE config 5: 10^6-cell TPM (3e7 entries), destination rows partitioned over the N GPUs
+    (cy2path_b200/rowpart.py: host order + label-propagation refinement, per-rank plans of the rank's own rows, fused
+    update + halo push over NVLink peer stores, device-side barrier per update). float64 iterate = the reference's
+    arithmetic (parity holds at any iteration count); the float32 iterate is listed beside it."""
+    import torch
+
+    from cy2path_b200 import rowpart
+    from cy2path_b200.synth import batched_starts
+
+    n = 1_000_000
+    T, _ = shared_graph(n, 5, rank, barrier)
+    t0 = time.perf_counter()
+    rp = rowpart.RowPartition(T, world, rank, device=dev.index, sweeps=8)
+    build_s = time.perf_counter() - t0
+    out = {"workload": "1,000,000 cells, 3e7 entries, rows of T^T partitioned over the GPUs", "n_gpus": world,
+           "collective": "none in NCCL: fused update + halo push (NVLink peer stores from the gather kernel) and a "
+                         "symmetric-memory signal barrier per update; one all-gather assembles the final iterate",
+           "partition": rp.summary(), "partition_build_s_host": build_s, "cases": []}
+    for B, dt, iters in ((1, torch.float64, 200), (256, torch.float64, 30), (256, torch.float32, 30)):
+        X0 = torch.from_numpy(batched_starts(T, B, seed=5)).to(dev).to(dt)
+        rowpart.propagate(rp, X0, 3, assemble=False)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rowpart.propagate(rp, X0, iters, assemble=False)
+        e1.record()
+        torch.cuda.synchronize()
+        # the timed call includes the one-off permutation of X0 and its inverse: subtract a zero-update call
+        z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        z0.record()
+        rowpart.propagate(rp, X0, 0, assemble=False)
+        z1.record()
+        torch.cuda.synchronize()
+        ms = _max_over_ranks(e0.elapsed_time(e1) - z0.elapsed_time(z1), dev, world)
+        es = X0.element_size()
+        recv = float(rp.halo.max()) * B * es
+        us = ms * 1e3 / iters
+        out["cases"].append({"B": B, "dtype": "f64" if es == 8 else "f32 (outside tolerance beyond ~60 updates)",
+                             "updates": iters, "us_per_update": us, "cell_iterations_per_s": n * B / (us * 1e-6),
+                             "nvlink_recv_bytes_per_update_fattest_rank": recv,
+                             "nvlink_recv_GBps_fattest_rank": (recv / (us * 1e-6) / 1e9) if world > 1 else 0.0,
+                             "nvlink_frac_of_900GBps": (recv / (us * 1e-6) / 1e9 / 900.0) if world > 1 else 0.0})
+        del X0
+    return out
+
+
+def ncu_reference(kernel_prefix, grid):
+    """dram bytes and L2 -> L1 sectors per launch of the dominant kernel from the committed ncu summary of this
+    round's capture (profiles/ncu_k1_current_summary.json, written by tools/ncu_summary.py); None when the capture is
+    of another kernel shape."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_k1_current_summary.json")))
+    except Exception:
+        return None
+    for rec in d.get("launches", []):
+        if kernel_prefix in rec.get("kernel", "") and rec.get("grid", "").replace(" ", "") == grid.replace(" ", ""):
+            return {"traffic": rec.get("dram_read_bytes", 0.0) + rec.get("dram_write_bytes", 0.0),
+                    "l2_to_l1_sectors": rec.get("l2_to_l1_read_sectors"), "l1_hit_pct": rec.get("l1_hit_pct"),
+                    "source": "profiles/ncu_k1_current_summary.json <- " + str(d.get("source"))}
+    return None
+
 
 
 # ------------------------------------------------------------------------------------------ B200 arm

@@ -676,3 +676,45 @@ int32_t cy2p_propagate_x(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t 
 }
 
 }  // extern "C"
+
+// ---- cross-GPU barrier between the updates of the row-partitioned run (cy2path_b200/rowpart.py) -------------------
+// One tiny kernel, stream-ordered after the rank's update kernel (whose peer stores are complete when it retires):
+// thread g of the single CTA writes this rank's epoch into slot `rank` of rank g's flag array (a peer store over
+// NVLink; its own slot for g == rank) and then spins until slot g of its OWN array shows that epoch: when every thread
+// is through, every rank's update of this round has retired. The epoch comes from a device counter the kernel itself
+// advances, so the launch has no per-call argument and can sit in a CUDA graph that is replayed for every pair of
+// updates (at B = 1 an update on 8 GPUs is ~10 us of work: the host-side launch path would otherwise bound it).
+// A rank that never arrives must not hang the others for good: the spin gives up after ~2 s and raises *d_error.
+namespace cy2p {
+__global__ void xbarrier_kernel(int32_t *const *peer_flags, volatile int32_t *my_flags, int32_t *epoch_counter,
+                                int32_t rank, int32_t world, int32_t *d_error) {
+    __shared__ int32_t s_epoch;
+    if (threadIdx.x == 0) s_epoch = ++(*epoch_counter);
+    __syncthreads();
+    const int32_t epoch = s_epoch;
+    const int g = threadIdx.x;
+    if (g < world) {
+        __threadfence_system();
+        *(volatile int32_t *)(peer_flags[g] + rank) = epoch;
+        const long long t0 = clock64();
+        while (my_flags[g] - epoch < 0) {
+            if (clock64() - t0 > 4000000000LL) {
+                atomicExch(d_error, 1);
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+}
+}  // namespace cy2p
+
+extern "C" int32_t cy2p_xbarrier(void *const *d_peer_flags, int32_t *d_my_flags, int32_t *d_epoch_counter, int32_t rank,
+                                 int32_t world, int32_t *d_error, void *stream) {
+    CY2P_REQUIRE(d_peer_flags && d_my_flags && d_epoch_counter && d_error, "null pointer");
+    CY2P_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "1 <= world <= 64 and 0 <= rank < world required");
+    count_launch();
+    xbarrier_kernel<<<1, 64, 0, (cudaStream_t)stream>>>((int32_t *const *)d_peer_flags, d_my_flags, d_epoch_counter, rank,
+                                                        world, d_error);
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}

@@ -284,3 +284,51 @@ int32_t ensure_reordered(cy2p_plan *plan, cudaStream_t st) {
 }
 
 }  // namespace cy2p
+
+// Host-only entry point (no device needed): the locality order of a CSR matrix, the same passes ensure_reordered runs
+// for a plan. The row-partitioned driver (cy2path_b200/rowpart.py) orders the WHOLE graph once on the host, cuts the
+// order into per-rank blocks and builds each rank's plan from its slice only, so no rank ever holds the whole T on
+// its device. order_out[q] = original cell id at position q. group <= 1 keeps the plain Cuthill-McKee order.
+extern "C" int32_t cy2p_order_host(int32_t n, int64_t nnz, const int32_t *h_indptr, const int32_t *h_indices,
+                                   int32_t group, int32_t *order_out) {
+    using namespace cy2p;
+    CY2P_REQUIRE(n >= 0 && nnz >= 0 && h_indptr && order_out && (nnz == 0 || h_indices), "null pointer / negative size");
+    if (h_indptr[0] != 0 || h_indptr[n] != nnz) {
+        set_error("indptr[0] must be 0 and indptr[n] == nnz");
+        return CY2P_ERR_BAD_CSR;
+    }
+    std::vector<int32_t> out_ptr(h_indptr, h_indptr + n + 1), out_idx(h_indices, h_indices + nnz), in_ptr((size_t)n + 1, 0);
+    for (int32_t i = 0; i < n; ++i)
+        if (out_ptr[i + 1] < out_ptr[i]) {
+            set_error("indptr is not monotone at row %d", i);
+            return CY2P_ERR_BAD_CSR;
+        }
+    for (int64_t p = 0; p < nnz; ++p) {
+        if (out_idx[p] < 0 || out_idx[p] >= n) {
+            set_error("column index %d out of range at entry %lld", out_idx[p], (long long)p);
+            return CY2P_ERR_BAD_CSR;
+        }
+        ++in_ptr[out_idx[p] + 1];
+    }
+    for (int32_t j = 0; j < n; ++j) in_ptr[j + 1] += in_ptr[j];
+    std::vector<Pair> in_pairs((size_t)nnz);
+    {
+        std::vector<int32_t> cur(in_ptr.begin(), in_ptr.end() - 1);
+        for (int32_t i = 0; i < n; ++i)
+            for (int32_t p = out_ptr[i]; p < out_ptr[i + 1]; ++p) in_pairs[cur[out_idx[p]]++] = Pair{i, 0.f};
+    }
+    std::vector<int32_t> order;
+    cuthill_mckee(n, out_ptr, out_idx, in_ptr, in_pairs, order);
+    if ((int32_t)order.size() != n) {
+        set_error("ordering failed");
+        return CY2P_ERR_INVALID_ARG;
+    }
+    if (group > 1) {
+        std::vector<int32_t> grouped;
+        grow_groups(n, group, out_ptr, out_idx, in_ptr, in_pairs, order, grouped);
+        if ((int32_t)grouped.size() == n) order.swap(grouped);
+    }
+    std::copy(order.begin(), order.end(), order_out);
+    return CY2P_OK;
+}
+

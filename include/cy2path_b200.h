@@ -128,6 +128,13 @@ int32_t cy2p_propagate_rows_ordered(cy2p_plan *plan, const float *d_Xp, float *d
 int32_t cy2p_propagate_rows_ordered_f64(cy2p_plan *plan, const double *d_Xp, double *d_Yp, int32_t B,
                                         int32_t q_begin, int32_t q_end, void *stream);
 
+/* Host-only (no device): the locality order a plan would build for this CSR matrix (Cuthill-McKee + groups of `group`
+ * cells that share sources; group <= 1: plain Cuthill-McKee). h_order_out[q] = original cell id at position q.
+ * Used by the row-partitioned driver to order the whole graph once on the host and give each rank a plan of its own
+ * row slice only (cy2path_b200/rowpart.py). */
+int32_t cy2p_order_host(int32_t n, int64_t nnz, const int32_t *h_indptr, const int32_t *h_indices, int32_t group,
+                        int32_t *h_order_out);
+
 /* Fused update + all-gather for the row partition: the kernel stores every finished row of [q_begin, q_end) into
  * ALL `npeers` next-iterate buffers (d_peer_out: device array of npeers base pointers, each an [n][B] iterate in
  * plan order; one of them is this rank's own, the others are peer-mapped over NVLink), so the exchange overlaps the
@@ -149,6 +156,15 @@ int32_t cy2p_propagate_rows_push_f64(cy2p_plan *plan, const double *d_Xp, void *
                                      const uint32_t *d_row_peers, int32_t B, int32_t q_begin, int32_t q_end,
                                      void *stream);
 int32_t cy2p_enable_peer_access(int32_t device, int32_t peer);
+
+/* Cross-GPU barrier between two updates of the row-partitioned run, as ONE small kernel on `stream` (so it orders
+ * after the rank's update kernel and can be captured in a CUDA graph): every rank writes its epoch into its slot of
+ * every rank's flag array (d_peer_flags: device array of `world` pointers to the ranks' int32[world] flag arrays in
+ * peer-mapped memory, this rank's own at index `rank`) and waits until its own array (d_my_flags) shows that epoch in
+ * every slot. The epoch is *d_epoch_counter + 1 (advanced by the kernel; all ranks must start from equal counters and
+ * zeroed flags). A wait that lasts ~2 s gives up and sets *d_error = 1 instead of hanging the device. */
+int32_t cy2p_xbarrier(void *const *d_peer_flags, int32_t *d_my_flags, int32_t *d_epoch_counter, int32_t rank,
+                      int32_t world, int32_t *d_error, void *stream);
 
 /* ---- K0/K2: chain sampling ------------------------------------------------------------------
  * cy2p_cdf_build replaces extract_nonzero_entries (simulation.py:15-53): idx int32 [n][W] and

@@ -21,6 +21,9 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("CY2PATH_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "cy2path")):
+    # the GPU box: the unmodified copies oracle/build_ref.py made in the build container (git-ignored build output)
+    REFERENCE_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def available() -> bool:
