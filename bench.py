@@ -420,7 +420,7 @@ def extra_config5(rank, world, dev, barrier):
            "partition": rp.summary(), "partition_build_s_host": build_s, "cases": []}
     for B, dt, iters in ((1, torch.float64, 200), (256, torch.float64, 30), (256, torch.float32, 30)):
         X0 = torch.from_numpy(batched_starts(T, B, seed=5)).to(dev).to(dt)
-        rowpart.propagate(rp, X0, 3, assemble=False)
+        rowpart.propagate(rp, X0, 9, assemble=False)  # warm-up (builds the CUDA graph of the B <= 8 path)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -570,9 +570,16 @@ def run_b200(args, w):
     achieved = bytes_per_launch / launch_s / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed ncu --set full
     # capture of `--workload profile` (same shapes and column tile as config2): profiles/README_r01.md section 5
-    traffic = None  # filled from the committed ncu capture of this round's kernel (profiles/)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel: parsed from the committed ncu capture of
+    # `--workload profile` (same shapes and column tile as config2), not a literal
+    ncu = None
+    if not single and xprec and args.workload in ("config2", "profile"):
+        cpl = int(os.environ.get("CY2PX_CPL", "8"))
+        ncu = ncu_reference("spmm_gather_x<%d, %d," % (16 if args.precision == "f48" else 8, cpl),
+                            "(%d, %d, 1)" % ((n + 63) // 64, min(tile, B) // (32 * cpl)))
+    traffic = ncu["traffic"] if ncu else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/ncu_spmm_gather_r01d_raw.csv" if traffic else None, "kernel": ("spmv_b1_persistent<double>" if single else
+                "traffic": traffic, "traffic_source": ncu["source"] if ncu else None, "kernel": ("spmv_b1_persistent<double>" if single else
                            "spmm_gather_x<%d,...>" % (16 if args.precision == "f48" else 8) if xprec else
                            "spmm_gather<%s,...>" % ("double" if args.precision == "fp64" else "float")),
                 "bytes_per_launch": bytes_per_launch,
@@ -581,8 +588,11 @@ def run_b200(args, w):
                 # nnz x columns x 4 B per update flow into the SMs; the part that misses L1 (290.1 M sectors per launch
                 # in the same ncu capture as `traffic`) leaves L2 at its measured output cap (~6,300 B/clk chip-wide,
                 # B300_MICROARCH.md "L2 cache"; 12.1 TB/s at 1.92 GHz)
-                "l2_gather_TBps": (None if single else T.nnz * min(tile, B) * 4 / launch_s / 1e12),
-                "l2_to_l1_TBps": (290.1e6 * 32 / launch_s / 1e12 if traffic else None),
+                "operand_bytes_per_element": (8 if single else {"f48": 6, "f40": 5, "fp64": 8, "fp32": 4}[args.precision]),
+                "l2_gather_TBps": (None if single else T.nnz * min(tile, B) *
+                                   {"f48": 6, "f40": 5, "fp64": 8, "fp32": 4}[args.precision] / launch_s / 1e12),
+                "l2_to_l1_TBps": (ncu["l2_to_l1_sectors"] * 32 / launch_s / 1e12 if ncu and ncu.get("l2_to_l1_sectors") else None),
+                "l1_hit_pct_ncu": (ncu.get("l1_hit_pct") if ncu else None),
                 "lts_cap_TBps": 6300 * 1.92e9 / 1e12,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (sustained copy)" if peaks else "fallback 6650 GB/s"}
 
@@ -636,7 +646,10 @@ def run_b200(args, w):
             d2h += w["chains"] * w["max_iter"] * 4 + w["chains"] * (w["max_iter"] - 1) * 4 + w["max_iter"] * n * 4
         e2e = {"value": world * cell_iters_per_gpu * args.steps / float(dt.item()), "unit": "cell-iterations/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": float(dt.item()) / args.steps * 1e3}
+               "ms_per_step": float(dt.item()) / args.steps * 1e3,
+               "notes": "host numpy inputs -> public API -> host numpy results, plan rebuilt every step; outside the "
+                        "timed region: pinning of the input arrays (done once) and the stationary vector (an input, "
+                        "estimate_stationary_state is stubbed with the precomputed one)"}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
@@ -651,6 +664,39 @@ def run_b200(args, w):
         if cr:
             cpu["chain_steps_per_s_1core_c_port"] = cr
 
+    # ---- the float32 iterate's rate, for the record: OUTSIDE the north_star tolerance at this iteration count
+    fp32_detail = None
+    if xprec and not single:
+        it32 = min(iters, 200)
+        _lib.propagate(plan, X0_d, 4, stationary=stat_d, want_final=True, want_eps=True)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        _lib.propagate(plan, X0_d, it32, stationary=stat_d, want_final=True, want_eps=True)
+        f1.record()
+        torch.cuda.synchronize()
+        ms32 = f0.elapsed_time(f1)
+        fp32_detail = {"label": "float32 iterate: outside the 1e-6 relative-L1 tolerance beyond ~60-100 iterations "
+                                "(3e-5 at 2,000), not the headline",
+                       "iterations_timed": it32, "cell_iterations_per_s_per_gpu": n * B * it32 / (ms32 * 1e-3),
+                       "hbm_roofline_frac": (8 * T.nnz + 4 * (n + 1) + 8 * n * B) * it32 / (ms32 * 1e-3) / 1e9 / peak}
+    torch.cuda.empty_cache()
+
+    extras = {}
+    if not args.no_extras and args.workload == "config2" and os.environ.get("CY2P_BENCH_EXTRAS", "1") != "0":
+        for name, fn in (("config3_fhmm", lambda: extra_config3(rank, dev, T, plan)),
+                         ("config4_strong", lambda: extra_config4(rank, world, dev, barrier, peak)),
+                         ("config5_rowpart", lambda: extra_config5(rank, world, dev, barrier))):
+            t_ex = time.perf_counter()
+            try:
+                r = fn()
+            except Exception as e:  # an extra must never cost the headline line
+                r = {"error": repr(e)[:300]}
+            if r is not None:
+                r["wall_s"] = time.perf_counter() - t_ex
+                extras[name] = r
+            torch.cuda.empty_cache()
+
     if rank == 0:
         line = {
             "metric": "msm_cell_iterations_per_s", "value": value, "unit": "cell-iterations/s", "n_gpus": world,
@@ -662,7 +708,8 @@ def run_b200(args, w):
             "detail": {"propagate_ms_per_step": prop_ms_avg, "chains_ms_per_step": chain_ms,
                        "chain_steps_per_s": (world * w["chains"] * (w["max_iter"] - 1) / (chain_ms * 1e-3)
                                              if has_chains and chain_ms > 0 else None),
-                       "propagate_cell_iterations_per_s": world * cell_iters_per_gpu / (prop_ms_avg * 1e-3)},
+                       "propagate_cell_iterations_per_s": world * cell_iters_per_gpu / (prop_ms_avg * 1e-3),
+                       "precision": args.precision, "fp32_outside_tolerance": fp32_detail, **extras},
         }
         emit(line)
     if world > 1:

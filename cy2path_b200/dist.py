@@ -248,9 +248,6 @@ def propagate_row_partitioned_fused(plan, X0, iters, group=None):
     return out
 
 
-_MASK_CACHE = {}
-
-
 def row_peer_masks(T, order, world):
     """For the row partition in the plan's order: uint32 mask per permuted row q, bit g set when rank g needs row q
     of the iterate — it owns q, or one of its destination rows has q as a source. ``T``: scipy CSR (T[i, j] moves
@@ -291,11 +288,12 @@ def propagate_row_partitioned_halo(plan, T, X0, iters, group=None):
     dev = X0.device
     order = plan_order(plan)
     m, blocks = row_blocks(n, world)
-    key = (int(plan.handle.value or 0), plan.n, plan.nnz, world)  # the C handle identifies the plan while it lives
-    if key not in _MASK_CACHE:  # host pass over the stored entries: once per (plan, world)
-        _MASK_CACHE.clear()
-        _MASK_CACHE[key] = torch.from_numpy(row_peer_masks(T, order.cpu().numpy(), world).view("int32")).to(dev)
-    masks = _MASK_CACHE[key]
+    # host pass over the stored entries, once per (plan, world); kept ON the plan object so the masks live and die
+    # with it (a cache keyed by the C handle's address could be hit by a later plan allocated at the same address)
+    cache = plan.__dict__.setdefault("_halo_masks", {})
+    if world not in cache:
+        cache[world] = torch.from_numpy(row_peer_masks(T, order.cpu().numpy(), world).view("int32")).to(dev)
+    masks = cache[world]
     with torch.cuda.device(dev):
         buf, ptrs, barrier = _symmetric_buffers((2, n, B), X0.dtype, dev, group)
         half = n * B * X0.element_size()

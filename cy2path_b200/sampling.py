@@ -19,25 +19,48 @@ logger = logging.getLogger("cy2path_b200")
 _PLAN_CACHE: dict = {}
 
 
+def _fingerprint(T):
+    """Content fingerprint of a scipy CSR matrix: sums over ALL stored values, column indices and row pointers (an
+    in-place edit of any entry changes at least one of them up to cancellation) plus a CRC of the head and tail of
+    each array. ~1 ms per million entries."""
+    import zlib
+
+    data, idx, ptr = np.asarray(T.data), np.asarray(T.indices), np.asarray(T.indptr)
+
+    def crc(a):
+        b = a.view(np.uint8).reshape(-1) if a.flags.c_contiguous else np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        return zlib.crc32(b[:65536].tobytes()) ^ zlib.crc32(b[-65536:].tobytes())
+
+    w = np.arange(1, 1 + min(data.size, 1 << 16), dtype=np.float64)  # position-weighted sample: catches swaps
+    stride = max(1, data.size // w.size)
+    samp = data[::stride][: w.size].astype(np.float64)
+    return (float(data.sum(dtype=np.float64)), float((samp * w[: samp.size]).sum()), int(idx.sum(dtype=np.int64)),
+            int(ptr.sum(dtype=np.int64)), crc(data), crc(idx), crc(ptr))
+
+
 def get_plan(T, device=None):
     """Plan (device copy of T, T^T, tables) for a scipy matrix, cached per matrix object.
 
-    The cache key includes the array addresses, nnz and a strided checksum of the values, so an
-    in-place edit of T rebuilds the plan."""
+    The cache holds a weak reference to the matrix (an entry dies with it, so a new matrix that reuses the id or the
+    buffers of a freed one cannot hit a stale plan) and keys on a fingerprint of the whole contents (`_fingerprint`),
+    so an in-place edit of T — e.g. making terminal rows absorbing through ``T.data[k] = ...`` — rebuilds the plan."""
+    import weakref
+
     import torch
 
     dev = torch.cuda.current_device() if device is None else device
-    data = np.asarray(T.data)
-    stride = max(1, data.size // 65536)
-    key = (id(T), dev, T.shape, int(T.nnz), data.ctypes.data, T.indices.ctypes.data,
-           float(data[::stride].sum(dtype=np.float64)))
-    hit = _PLAN_CACHE.get(id(T))
-    if hit is not None and hit[0] == key:
+    key = (dev, T.shape, int(T.nnz), np.asarray(T.data).dtype.str) + _fingerprint(T)
+    hit = _PLAN_CACHE.get((id(T), dev))
+    if hit is not None and hit[0] == key and hit[2]() is T:
         return hit[1]
     plan = _lib.Plan(T, device=dev)
     if len(_PLAN_CACHE) >= 4:
         _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
-    _PLAN_CACHE[id(T)] = (key, plan)
+    try:
+        ref = weakref.ref(T, lambda _r, k=(id(T), dev): _PLAN_CACHE.pop(k, None))
+    except TypeError:  # not weak-referenceable: keep a strong reference (the cache is 4 entries deep)
+        ref = (lambda t: (lambda: t))(T)
+    _PLAN_CACHE[(id(T), dev)] = (key, plan, ref)
     return plan
 
 

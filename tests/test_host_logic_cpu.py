@@ -58,3 +58,32 @@ def test_subspace_iteration_single_and_degenerate_eigenvalue():
     vals, V, info = dominant_left_eigenpairs(lambda X: torch.from_numpy(Tt @ X.numpy()), 1500)
     assert info["converged"] and len(vals) == len(eigs(g["T"])[0]) and len(vals) > 1
     assert np.allclose(vals, 1.0, atol=1e-6) and V.shape == (1500, len(vals))
+
+
+def test_plan_cache_fingerprint_sees_in_place_edits():
+    """the plan cache key must change when T is edited in place (values, column indices or row pointers),
+    also far from a strided sample of the values."""
+    import scipy.sparse as sp
+
+    from cy2path_b200.sampling import _fingerprint
+
+    rng = np.random.default_rng(0)
+    T = sp.random(3000, 3000, density=0.03, format="csr", random_state=1, dtype=np.float32)
+    assert T.nnz > 200_000
+    base = _fingerprint(T)
+    assert _fingerprint(T) == base
+    for k in rng.integers(0, T.nnz, 20):
+        old = T.data[k]
+        T.data[k] = old * 0.5 + 0.125  # e.g. making a terminal row absorbing
+        assert _fingerprint(T) != base
+        T.data[k] = old
+    assert _fingerprint(T) == base
+    k = int(rng.integers(1, T.nnz - 1))
+    old = T.indices[k]
+    T.indices[k] = (old + 1) % 3000
+    assert _fingerprint(T) != base
+    T.indices[k] = old
+    a, b = T.data[10], T.data[11]
+    if a != b:  # swapping two values keeps the plain sum; the position-weighted sample or the CRC must catch it
+        T.data[10], T.data[11] = b, a
+        assert _fingerprint(T) != base
