@@ -310,7 +310,8 @@ def extra_config4(rank, world, dev, barrier, peak_gbs):
     plan = _lib.Plan(T)
     stat = torch.from_numpy(stationary_by_power(T, 50)).to(dev)
     X0 = torch.from_numpy(batched_starts(T, Bl, seed=4 + 1000 * rank)).to(dev)
-    _lib.propagate_x(plan, X0, 6, stationary=stat, want_eps=True)  # builds the ordering, warms up
+    # warm-up; long enough that the plan builds its locality ordering here (B * iters >= 4096), not in the timed call
+    _lib.propagate_x(plan, X0, max(6, 4096 // Bl + 2), stationary=stat, want_eps=True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
