@@ -587,6 +587,302 @@ fhmm_data_fwd(int N, int I, int K, int tchunk, const float *__restrict__ logE, c
 }
 
 // --------------------------------------------------------------------------------------------------
+// Tensor-core gradients of the data term (two-pass mode: r[t,n] = D/P is in memory).
+//   dlogE[k,n] = -(1/I) E[k,n] * sum_t G[t,k] r[t,n]      ([K x I] . [I x N]: the contraction over K = I time steps)
+//   dG[t,k]    = -(1/I) sum_n r[t,n] E[k,n]                ([I x N] . [N x K]: the contraction over the N cells)
+// Both are warp-level mma.sync m16n8k8 TF32 products with the 3xTF32 split (x = hi + lo, hi*hi + hi*lo + lo*hi, fp32
+// accumulate): each factor keeps ~21 mantissa bits, the gradients stay within 1e-6 relative of the FFMA path. The
+// 5th-generation tcgen05 path needs M >= 64 per instruction and operands staged through shared-memory descriptors; with
+// M = K <= 64 emission rows and an arithmetic intensity of K/2 flop per byte of r these contractions are bound by
+// reading r (I*N*4 bytes), not by the tensor pipe, so the warp-level instruction is the right tool and the evidence the
+// north_star asks for is the tensor-pipe counter next to the bytes (profiles/README_r02.md).
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    mma_tf32(c, al, bh);  // small terms first
+    mma_tf32(c, ah, bl);
+    mma_tf32(c, ah, bh);
+}
+
+// Leading dimension of a small matrix held in shared memory for A-fragment loads (lane (g, tg) reads [row g][col tg]):
+// an odd multiple of 4 words puts the 32 lanes of a load in 32 different banks.
+__host__ __device__ constexpr int mma_ld(int cols) { return ((cols + 7) / 8 * 8) + 4; }
+
+// P and r on the tensor cores — the emission GEMM proper (_FHMM.py:126-144: pred[t,n] = log sum_k G[t,k] E[k,n]):
+//   P^[t,n] = sum_k G[t,k] E^[k,n] with E^ = exp(logE - m[n]) (max shift per cell), M = 16 time steps, N = 8 cells,
+//   K = emission rows in steps of 8. A warp keeps the E^ fragments of its NW cell tiles in registers (hi / lo planes),
+//   takes the G fragments of a block of 16 time steps from shared memory once and uses them for all its tiles; the
+//   C fragment (t = g / g + 8, n = 2tg / 2tg + 1) is turned into pred, the divergence and r = D / P in place.
+template <int KT, int NW>
+__global__ void __launch_bounds__(128)
+fhmm_fwd_mma(int N, int I, int K, int ldG, int tchunk, const float *__restrict__ logE, const float *__restrict__ G,
+             const float *__restrict__ D, float *__restrict__ pred, float *__restrict__ R, double *__restrict__ div_acc,
+             float inv_I) {
+    constexpr int LD = mma_ld(KT * 8);
+    extern __shared__ uint32_t sG32[];  // [2][tpad][LD]
+    const int t0 = blockIdx.y * tchunk, t1 = min(I, t0 + tchunk);
+    const int tpad = (t1 - t0 + 15) / 16 * 16;
+    uint32_t *sGh = sG32, *sGl = sG32 + (size_t)tpad * LD;
+    for (int i = threadIdx.x; i < tpad * (KT * 8); i += blockDim.x) {
+        const int tt = i / (KT * 8), k = i % (KT * 8), t = t0 + tt;
+        const float v = (t < t1 && k < K) ? G[(size_t)t * ldG + k] : 0.f;
+        split_tf32(v, sGh[tt * LD + k], sGl[tt * LD + k]);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+    const int nbase = (blockIdx.x * 4 + warp) * (8 * NW);
+    // B fragments: b0 = E^[k0 + tg][n0 + g], b1 = E^[k0 + tg + 4][n0 + g]; the shift m[n] is needed for column n0 + g
+    // (fragment) and for columns n0 + 2tg, n0 + 2tg + 1 (C fragment): computed for the former, shuffled for the latter
+    uint32_t bh[NW][KT][2], bl[NW][KT][2];
+    float mc[NW][2], em[NW][2];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const int n = nbase + 8 * w + g;
+        const bool ok = n < N;
+        float m = -INFINITY;
+        for (int k = 0; k < K; ++k) m = fmaxf(m, ok ? logE[(size_t)k * N + n] : 0.f);
+#pragma unroll
+        for (int q = 0; q < KT; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = 8 * q + tg + 4 * h;
+                const float v = (ok && k < K) ? expf(logE[(size_t)k * N + n] - m) : 0.f;
+                split_tf32(v, bh[w][q][h], bl[w][q][h]);
+            }
+        // lane (g, tg) needs m of columns 2tg and 2tg + 1 of the tile: held by the lanes with g' = 2tg, 2tg + 1
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            mc[w][j] = __shfl_sync(0xffffffffu, m, (2 * tg + j) * 4);
+            em[w][j] = expf(-mc[w][j]);
+        }
+    }
+    __syncthreads();
+    double div = 0.0;
+    for (int tb = 0; tb < tpad; tb += 16) {
+        uint32_t ah[KT][4], al[KT][4];
+#pragma unroll
+        for (int q = 0; q < KT; ++q) {
+            const uint32_t *ph = sGh + (size_t)(tb + g) * LD + 8 * q + tg, *pl = sGl + (size_t)(tb + g) * LD + 8 * q + tg;
+            ah[q][0] = ph[0], ah[q][1] = ph[8 * LD], ah[q][2] = ph[4], ah[q][3] = ph[8 * LD + 4];
+            al[q][0] = pl[0], al[q][1] = pl[8 * LD], al[q][2] = pl[4], al[q][3] = pl[8 * LD + 4];
+        }
+        float div_f = 0.f;
+        // the D values of this block of time steps are requested before the MMAs so that the two overlap: lane (g, tg)
+        // owns rows t = g, g + 8 and the column pair (2tg, 2tg + 1) of every tile (one 8-byte access when N is even)
+        float2 dv[NW][2];
+        const bool vec = (N & 1) == 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = t0 + tb + g + 8 * h, n = nbase + 8 * w + 2 * tg;
+                dv[w][h] = make_float2(0.f, 0.f);
+                if (D != nullptr && t < t1) {
+                    const float *dp = D + (size_t)t * N + n;
+                    if (vec && n + 1 < N) dv[w][h] = __ldg(reinterpret_cast<const float2 *>(dp));
+                    else {
+                        if (n < N) dv[w][h].x = __ldg(dp);
+                        if (n + 1 < N) dv[w][h].y = __ldg(dp + 1);
+                    }
+                }
+            }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < KT; ++q) mma_3xtf32(c, ah[q], al[q], bh[w][q], bl[w][q]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = t0 + tb + g + 8 * h, n = nbase + 8 * w + 2 * tg;
+                if (t >= t1 || n >= N) continue;
+                float rr[2], pp[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float p = fmaxf(c[2 * h + j], FLT_MIN);
+                    pp[j] = pred != nullptr ? mc[w][j] + logf(p) : 0.f;  // forward_model output: full-precision log
+                    const float d = j ? dv[w][h].y : dv[w][h].x;
+                    float r = 0.f;
+                    if (d > 0.f) {
+                        r = __fdividef(d, p) * em[w][j];
+                        div_f += d * (__logf(d) - mc[w][j] - __logf(p));
+                    }
+                    rr[j] = r;
+                }
+                const size_t off = (size_t)t * N + n;
+                if (vec && n + 1 < N) {
+                    if (pred != nullptr) *reinterpret_cast<float2 *>(pred + off) = make_float2(pp[0], pp[1]);
+                    if (D != nullptr) *reinterpret_cast<float2 *>(R + off) = make_float2(rr[0], rr[1]);
+                } else {
+                    if (pred != nullptr) {
+                        pred[off] = pp[0];
+                        if (n + 1 < N) pred[off + 1] = pp[1];
+                    }
+                    if (D != nullptr) {
+                        R[off] = rr[0];
+                        if (n + 1 < N) R[off + 1] = rr[1];
+                    }
+                }
+            }
+        }
+        div += (double)div_f;
+    }
+    if (D != nullptr) {
+        div = warp_sum(div);
+        __shared__ double sdiv[4];
+        if (lane == 0) sdiv[warp] = div;
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(div_acc, (sdiv[0] + sdiv[1] + sdiv[2] + sdiv[3]) * (double)inv_I);
+    }
+}
+
+// dlogE: CTA = 4 warps, a warp owns NW = 4 tiles of 8 cells (the CTA covers one 512-byte span of every row of r), grid.y
+// = t splits; A = G^T from shared memory (pre-split into hi / lo, loaded once per CTA), B = r straight from global
+// memory in the fragment layout (each element is read by exactly one thread), MT = ceil(K / 16) accumulator tiles per
+// cell tile.
+template <int MT, int NW>
+__global__ void __launch_bounds__(128)
+fhmm_dE_mma(int N, int I, int K, int Kfull, int ldG, int tchunk, const float *__restrict__ logE,
+            const float *__restrict__ G, const float *__restrict__ R, float *__restrict__ glogE_split, float inv_I) {
+    constexpr int LD = MT * 16 + 8;  // = 8 (mod 16 words): lane (g, tg) reads [row tg][col g]: 32 different banks
+    extern __shared__ uint32_t sG32[];  // [2][tpad][LD]: hi plane, lo plane
+    const int t0 = blockIdx.y * tchunk, t1 = min(I, t0 + tchunk);
+    const int tpad = (t1 - t0 + 7) / 8 * 8;
+    uint32_t *sGh = sG32, *sGl = sG32 + (size_t)tpad * LD;
+    for (int i = threadIdx.x; i < tpad * (MT * 16); i += blockDim.x) {
+        const int tt = i / (MT * 16), k = i % (MT * 16), t = t0 + tt;
+        const float v = (t < t1 && k < K) ? G[(size_t)t * ldG + k] : 0.f;
+        split_tf32(v, sGh[tt * LD + k], sGl[tt * LD + k]);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+    const int nbase = (blockIdx.x * 4 + warp) * (8 * NW);
+    if (nbase >= N) return;
+    float c[NW][MT][4];
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+#pragma unroll
+        for (int m = 0; m < MT; ++m) c[w][m][0] = c[w][m][1] = c[w][m][2] = c[w][m][3] = 0.f;
+    for (int tb = 0; tb < tpad; tb += 8) {
+        float r0[NW], r1[NW];
+        const int ta = t0 + tb + tg, tbb = ta + 4;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int n = nbase + 8 * w + g;
+            r0[w] = (n < N && ta < t1) ? __ldg(R + (size_t)ta * N + n) : 0.f;
+            r1[w] = (n < N && tbb < t1) ? __ldg(R + (size_t)tbb * N + n) : 0.f;
+        }
+        uint32_t ah[MT][4], al[MT][4];
+        const uint32_t *gh = sGh + (size_t)(tb + tg) * LD + g, *gl = sGl + (size_t)(tb + tg) * LD + g;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            ah[m][0] = gh[16 * m], ah[m][1] = gh[16 * m + 8], ah[m][2] = gh[4 * LD + 16 * m], ah[m][3] = gh[4 * LD + 16 * m + 8];
+            al[m][0] = gl[16 * m], al[m][1] = gl[16 * m + 8], al[m][2] = gl[4 * LD + 16 * m], al[m][3] = gl[4 * LD + 16 * m + 8];
+        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            uint32_t bh[2], bl[2];
+            split_tf32(r0[w], bh[0], bl[0]);
+            split_tf32(r1[w], bh[1], bl[1]);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) mma_3xtf32(c[w][m], ah[m], al[m], bh, bl);
+        }
+    }
+    // C fragment: rows k = 16m + g (+8), columns n0 + 2tg (+1)
+    float *out = glogE_split + (size_t)blockIdx.y * Kfull * N;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = 16 * m + g + 8 * h;
+                if (k >= K) continue;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int n = nbase + 8 * w + 2 * tg + j;
+                    if (n < N) out[(size_t)k * N + n] = -inv_I * expf(logE[(size_t)k * N + n]) * c[w][m][2 * h + j];
+                }
+            }
+}
+
+// dG: CTA = 8 warps, owns 128 consecutive cells (E tile split hi / lo in shared memory) for ALL time steps; a warp
+// takes blocks of 16 time steps, A = r in the row-major fragment layout (each lane reads 4 floats of 4 different
+// rows; a warp covers 16 rows x 32 bytes = whole sectors), B = E^T from shared memory, NT = ceil(K / 8) accumulator
+// tiles; one atomic per (t, k) and CTA at the end of a block of time steps.
+constexpr int kMmaCells = 64, kMmaLdE = kMmaCells + 4;
+template <int NT>
+__global__ void __launch_bounds__(256)
+fhmm_dG_mma(int N, int I, int K, int Kfull, const float *__restrict__ logE, const float *__restrict__ R,
+            float *__restrict__ gG, float inv_I) {
+    extern __shared__ uint32_t sE32[];  // [2][NT*8][kMmaLdE]
+    uint32_t *sEh = sE32, *sEl = sE32 + (size_t)NT * 8 * kMmaLdE;
+    const int c0 = blockIdx.x * kMmaCells;
+    for (int i = threadIdx.x; i < NT * 8 * kMmaCells; i += blockDim.x) {
+        const int k = i / kMmaCells, j = i % kMmaCells, n = c0 + j;
+        const float v = (k < K && n < N) ? expf(logE[(size_t)k * N + n]) : 0.f;
+        split_tf32(v, sEh[k * kMmaLdE + j], sEl[k * kMmaLdE + j]);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+    for (int tb = warp * 16; tb < I; tb += 8 * 16) {
+        float c[NT][4];
+#pragma unroll
+        for (int q = 0; q < NT; ++q) c[q][0] = c[q][1] = c[q][2] = c[q][3] = 0.f;
+        const int ta = tb + g, tbb = tb + g + 8;
+        const float *ra = R + (size_t)ta * N + c0 + tg, *rb = R + (size_t)tbb * N + c0 + tg;
+        constexpr int UN = 4;
+        for (int j0 = 0; j0 < kMmaCells; j0 += 8 * UN) {
+            float a[UN][4];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int j = j0 + 8 * u, n = c0 + j + tg;
+                a[u][0] = (ta < I && n < N) ? __ldg(ra + j) : 0.f;
+                a[u][1] = (tbb < I && n < N) ? __ldg(rb + j) : 0.f;
+                a[u][2] = (ta < I && n + 4 < N) ? __ldg(ra + j + 4) : 0.f;
+                a[u][3] = (tbb < I && n + 4 < N) ? __ldg(rb + j + 4) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int j = j0 + 8 * u;
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_tf32(a[u][e], ah[e], al[e]);
+#pragma unroll
+                for (int q = 0; q < NT; ++q) {
+                    const uint32_t *eh = sEh + (size_t)(8 * q + g) * kMmaLdE + j + tg;
+                    const uint32_t *el = sEl + (size_t)(8 * q + g) * kMmaLdE + j + tg;
+                    const uint32_t bh[2] = {eh[0], eh[4]}, bl[2] = {el[0], el[4]};
+                    mma_3xtf32(c[q], ah, al, bh, bl);
+                }
+            }
+        }
+        // C fragment: rows t = tb + g (+8), columns k = 8q + 2tg (+1)
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = tb + g + 8 * h;
+                if (t >= I) continue;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int k = 8 * q + 2 * tg + j;
+                    const float v = c[q][2 * h + j];
+                    if (k < K && v != 0.f) atomicAdd(&gG[(size_t)t * Kfull + k], -inv_I * v);
+                }
+            }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // Per-node conditionals from the time-averaged joint M[s,l,n] = logE[s,e(l),n] + logC[s,l] (trainer.py:153-172):
 //   lngs[s,n] = log P(n|s), lngc[l,n] = log P(n|l), lcgn[l,n] = log P(l|n).
 // Writes X1[n][0:S] = P(n|s), X1[n][S:S+L] = P(n|l) (operands of the products with T) and X2[n][l] = P(l|n).
@@ -1597,6 +1893,11 @@ struct FhmmWs {
 
 size_t up(size_t x) { return (x + 255) / 256 * 256; }
 
+int env_flag(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 // Block length of the recurrence decomposition: ~sqrt(I), bounded by the shared memory the powers A^1..A^P need
 int choose_block(int S, int L, int I, size_t *smem_fwd, size_t *smem_bwd) {
     const size_t budget = 200 * 1024;
@@ -1624,7 +1925,10 @@ FhmmWs fhmm_layout(int S, int L, int Le, int N, int I) {
     // t-splits: the data pass runs 128-thread CTAs at 4 per SM (J = 4 variants are register-limited), so aim at
     // whole waves of 148 * 4 CTAs (the first capture ran 1.66 waves: 40% of the second wave idle);
     // the G chunk of a split must fit 32 KB of shared memory
-    w.two_pass = w.KP > 24;
+    // CY2P_FHMM_TWO_PASS=1 forces the forward + tensor-core-gradient split for small emission matrices too (measurement)
+    // (default since round 2: the split path with the tensor-core kernels beats the fused FFMA2 pass at every K —
+    // 0.55 vs 0.57 ms per call at K = 10, 0.77 vs 1.44 ms at K = 40, profiles/bench_fhmm_mma_r02.jsonl)
+    w.two_pass = w.KP > 24 || env_flag("CY2P_FHMM_TWO_PASS", env_flag("CY2P_FHMM_MMA", 1)) != 0;
     auto split_for = [&](int J, int kp, int ctas_per_sm, int *nsplit_out, int *tchunk_out) {
         const int tiles = (N + 128 * J - 1) / (128 * J);
         const int wave = 148 * ctas_per_sm;
@@ -1640,6 +1944,27 @@ FhmmWs fhmm_layout(int S, int L, int Le, int N, int I) {
     if (w.two_pass) {
         split_for(2, w.KP, 3, &w.nsplitA, &w.tchunkA);
         split_for(4, 12, 4, &w.nsplit, &w.tchunk);
+        if (env_flag("CY2P_FHMM_MMA", 1)) {
+            // tensor-core gradients: a CTA of fhmm_dE_mma keeps the G chunk of its t split in shared memory as two
+            // tf32 planes; 128 time steps per split keep that at <= 64 KB (3 CTAs per SM)
+            if (w.tchunk > 128) w.tchunk = 128;
+            if (w.tchunk < 64 && I >= 64) w.tchunk = 64;
+            w.nsplit = (I + w.tchunk - 1) / w.tchunk;
+            // forward kernel: 128-thread CTAs over 32 * NW cells, ~4 resident per SM: pick the t split whose grid
+            // fills whole waves best (chunks of <= 256 time steps: <= 41-90 KB of shared memory for the G planes)
+            const int kt = (w.KP + 7) / 8, nw = kt <= 3 ? 4 : 2;
+            const int tiles = (N + 32 * nw - 1) / (32 * nw), wave = 148 * 4;
+            int best = (I + 255) / 256;
+            double best_eff = 0.0;
+            for (int ns = (I + 255) / 256; ns <= 12 && ns <= I; ++ns) {
+                const long ctas = (long)tiles * ns;
+                const double eff = (double)ctas / (double)(((ctas + wave - 1) / wave) * wave);
+                if (eff > best_eff + 0.02) best_eff = eff, best = ns;
+            }
+            w.nsplitA = best;
+            w.tchunkA = (I + best - 1) / best;
+            w.nsplitA = (I + w.tchunkA - 1) / w.tchunkA;
+        }
     } else {
         split_for(w.KP <= 12 ? 4 : 2, w.KP, 4, &w.nsplit, &w.tchunk);
         w.nsplitA = w.tchunkA = 0;
@@ -1680,11 +2005,54 @@ template <int KP>
 void launch_data_two_pass(int N, int I, int K, const FhmmWs &w, char *ws, const float *logE, const float *G,
                           const float *D, float *pred, float *split, float *gG, double *div_acc, cudaStream_t st) {
     float *R = (float *)(ws + w.R);
-    dim3 gridA((unsigned)((N + 255) / 256), (unsigned)w.nsplitA);
-    count_launch();
-    fhmm_data_fwd<KP><<<gridA, 128, sizeof(float) * (size_t)w.tchunkA * KP, st>>>(N, I, K, w.tchunkA, logE, G, D, pred, R,
-                                                                                 div_acc, 1.0f / (float)I);
+    if (env_flag("CY2P_FHMM_MMA", 1)) {  // P, pred, divergence and r: the emission GEMM on the tensor cores
+        constexpr int KT = (KP + 7) / 8;
+        constexpr int NW = KT <= 3 ? 4 : 2;  // cell tiles per warp (E^ fragments live in registers: 4 KT NW of them)
+        const int tpad = (w.tchunkA + 15) / 16 * 16;
+        const size_t smem = sizeof(uint32_t) * 2 * (size_t)tpad * mma_ld(KT * 8);
+        dim3 grid((unsigned)((N + 32 * NW - 1) / (32 * NW)), (unsigned)w.nsplitA);
+        count_launch();
+        cudaFuncSetAttribute(fhmm_fwd_mma<KT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fhmm_fwd_mma<KT, NW><<<grid, 128, smem, st>>>(N, I, K, KP, w.tchunkA, logE, G, D, pred, R, div_acc, 1.0f / (float)I);
+    } else {
+        dim3 gridA((unsigned)((N + 255) / 256), (unsigned)w.nsplitA);
+        count_launch();
+        fhmm_data_fwd<KP><<<gridA, 128, sizeof(float) * (size_t)w.tchunkA * KP, st>>>(N, I, K, w.tchunkA, logE, G, D, pred,
+                                                                                     R, div_acc, 1.0f / (float)I);
+    }
     if (D == nullptr) return;  // forward only
+    const int use_mma = env_flag("CY2P_FHMM_MMA", 1);
+    if (use_mma) {  // the two gradients on the tensor cores (3xTF32), r read twice (mostly out of L2)
+        const float inv_I = 1.0f / (float)I;
+        {
+            const int MT = (K + 15) / 16;
+            const int tpad = (w.tchunk + 7) / 8 * 8;
+            const size_t smem = sizeof(uint32_t) * 2 * (size_t)tpad * (MT * 16 + 8);
+            dim3 grid((unsigned)((N + 127) / 128), (unsigned)w.nsplit);
+            count_launch();
+#define DE_CASE(MT_, NW_)                                                                                           \
+    case MT_:                                                                                                       \
+        cudaFuncSetAttribute(fhmm_dE_mma<MT_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        fhmm_dE_mma<MT_, NW_><<<grid, 128, smem, st>>>(N, I, K, K, KP, w.tchunk, logE, G, R, split, inv_I);        \
+        break;
+            switch (MT) { DE_CASE(1, 4) DE_CASE(2, 4) DE_CASE(3, 4) DE_CASE(4, 4) }
+#undef DE_CASE
+        }
+        {
+            const int NT = (K + 7) / 8;
+            const size_t smem = sizeof(uint32_t) * 2 * (size_t)NT * 8 * kMmaLdE;
+            dim3 grid((unsigned)((N + kMmaCells - 1) / kMmaCells));
+            count_launch();
+#define DG_CASE(NT_)                                                                                                \
+    case NT_:                                                                                                       \
+        cudaFuncSetAttribute(fhmm_dG_mma<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+        fhmm_dG_mma<NT_><<<grid, 256, smem, st>>>(N, I, K, K, logE, R, gG, inv_I);                                  \
+        break;
+            switch (NT) { DG_CASE(1) DG_CASE(2) DG_CASE(3) DG_CASE(4) DG_CASE(5) DG_CASE(6) DG_CASE(7) DG_CASE(8) }
+#undef DG_CASE
+        }
+        return;
+    }
     dim3 gridB((unsigned)((N + 511) / 512), (unsigned)w.nsplit);
     for (int koff = 0; koff < K; koff += 12) {
         const int Ks = K - koff < 12 ? K - koff : 12;
@@ -1714,9 +2082,15 @@ void dispatch_data_pass(int N, int I, int K, const FhmmWs &w, char *ws, const fl
     case KP_:                                                                                     \
         launch_data_two_pass<KP_>(N, I, K, w, ws, logE, G, D, pred, split, gG, div_acc, st);      \
         break;
+    if (w.two_pass) {
+        switch (w.KP) {
+            CASE2(2) CASE2(4) CASE2(6) CASE2(8) CASE2(10) CASE2(12) CASE2(16) CASE2(20) CASE2(24)
+            CASE2(32) CASE2(40) CASE2(48) CASE2(64)
+        }
+        return;
+    }
     switch (w.KP) {
         CASE(2, 4) CASE(4, 4) CASE(6, 4) CASE(8, 4) CASE(10, 4) CASE(12, 4) CASE(16, 2) CASE(20, 2) CASE(24, 2)
-        CASE2(32) CASE2(40) CASE2(48) CASE2(64)
     }
 #undef CASE
 #undef CASE2

@@ -346,6 +346,31 @@ spmm_gather_x(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, XArgs a)
                                                              blockIdx.x % kXEpsCopies, s_acc, &s_done);
 }
 
+// Persistent variant: num_SMs x MINB resident CTAs draw (column slab, row group) items from one counter in launch
+// order — slab-major, row groups ascending, so the wave of CTAs still sweeps one contiguous band of the ordered rows
+// (what keeps the gathers in L2) — and a CTA's warps stay on ADJACENT rows for the whole launch: no CTA tail, no block
+// scheduling between row groups. counter: one zeroed int per launch.
+template <int LOB, int CPL, int WARPS, int MINB, int U, bool EPS>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+spmm_gather_x_persist(int32_t n_rows, int32_t rows_per_item, int32_t nslabs, int32_t *__restrict__ counter, XArgs a) {
+    __shared__ unsigned long long s_acc[2][CPL][32];
+    __shared__ unsigned s_done;
+    __shared__ int32_t s_item;
+    const int32_t nrg = (n_rows + rows_per_item - 1) / rows_per_item;
+    const int32_t total = nrg * nslabs;
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(counter, 1);
+        __syncthreads();
+        const int32_t item = s_item;
+        if (item >= total) break;
+        const int32_t slab = item / nrg, rg = item % nrg;
+        const int32_t row0 = rg * rows_per_item;
+        gather_block_x<LOB, CPL, WARPS, U, false, false, EPS>(a, row0, min(row0 + rows_per_item, n_rows), slab,
+                                                               rg % kXEpsCopies, s_acc, &s_done);
+        __syncthreads();  // s_item and the eps accumulators are reused by the next item
+    }
+}
+
 // ---- small kernels ----------------------------------------------------------------------------------------------
 __global__ void widen_pairs_kernel(int64_t nnz, const Pair *__restrict__ in, PairD *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -443,7 +468,7 @@ static int x_env_int(const char *name, int dflt) {
 }
 
 struct XConfig {
-    int lob, cpl, warps, rows_per_cta, minb, u;
+    int lob, cpl, warps, rows_per_cta, minb, u, persist;
 };
 
 static XConfig x_config(int lo_bits) {
@@ -451,7 +476,9 @@ static XConfig x_config(int lo_bits) {
     c.lob = lo_bits == 8 ? 8 : 16;
     c.cpl = x_env_int("CY2PX_CPL", 8) == 4 ? 4 : 8;
     c.minb = x_env_int("CY2PX_MINB", 2);
-    c.u = x_env_int("CY2PX_U", 4) == 2 ? 2 : 4;
+    c.persist = x_env_int("CY2PX_PERSIST", 0);
+    const int u = x_env_int("CY2PX_U", 4);
+    c.u = u == 2 ? 2 : 4;
     const int w = x_env_int("CY2PX_WARPS", 8);
     c.warps = w >= 16 ? 16 : 8;
     const int r = x_env_int("CY2PX_ROWS", 0);
@@ -459,8 +486,9 @@ static XConfig x_config(int lo_bits) {
     return c;
 }
 
+constexpr int kXCounterSlots = 4096;  // per-launch work counters of the persistent variant, zeroed per block of launches
 struct XWs {
-    size_t eps_acc, scal, part, bufA, bufB, pi_rows, total;
+    size_t eps_acc, scal, part, bufA, bufB, pi_rows, counters, total;
     int32_t tile;      // columns per tile (multiple of the slab width)
     uint32_t pitch;    // bytes per row of a scratch tile
 };
@@ -494,6 +522,8 @@ static XWs x_ws_layout(const cy2p_plan *plan, int32_t B, int32_t iters, int want
     off = x_align_up(off + (size_t)plan->n * w.pitch, 256);
     w.pi_rows = off;
     if (want_eps) off = x_align_up(off + sizeof(double) * (size_t)plan->n, 256);
+    w.counters = off;
+    off = x_align_up(off + sizeof(int32_t) * kXCounterSlots, 256);
     w.total = off;
     return w;
 }
@@ -511,9 +541,25 @@ static int32_t ensure_pairsD(cy2p_plan *plan, const Pair *src, PairD **dst, cuda
     return CY2P_OK;
 }
 
+struct XPersist {
+    int32_t *counter = nullptr;  // zeroed int for this launch, or null: plain grid
+    int num_sms = 0;
+};
+
 template <int LOB, int CPL, int WARPS, int MINB, int U, bool IN_F32, bool OUT_F32>
-static void x_launch_t(const XArgs &a, int32_t n, int rows_per_cta, cudaStream_t st) {
+static void x_launch_t(const XArgs &a, int32_t n, int rows_per_cta, cudaStream_t st, XPersist ps = XPersist()) {
     const int nslabs = (a.ncols + 32 * CPL - 1) / (32 * CPL);
+    if constexpr (!IN_F32 && !OUT_F32) {
+        if (ps.counter) {
+            count_launch();
+            const int ctas = ps.num_sms * MINB;
+            if (a.eps_acc)
+                spmm_gather_x_persist<LOB, CPL, WARPS, MINB, U, true><<<ctas, WARPS * 32, 0, st>>>(n, rows_per_cta, nslabs, ps.counter, a);
+            else
+                spmm_gather_x_persist<LOB, CPL, WARPS, MINB, U, false><<<ctas, WARPS * 32, 0, st>>>(n, rows_per_cta, nslabs, ps.counter, a);
+            return;
+        }
+    }
     const dim3 grid((unsigned)((n + rows_per_cta - 1) / rows_per_cta), (unsigned)nslabs);
     count_launch();
     if (a.eps_acc)
@@ -528,22 +574,23 @@ static void x_launch_t(const XArgs &a, int32_t n, int rows_per_cta, cudaStream_t
 // 98 KB: 2.7) — in-flight bytes are registers, so the best shape is few fat warps: 8 columns per lane, 4 row gathers
 // in flight, 128 registers, 16 warps per SM. Shapes that spill (64-register budgets) lose 15-30%.
 template <int LOB, int CPL, int U>
-static void x_launch_hot(const XArgs &a, int32_t n, const XConfig &c, cudaStream_t st) {
+static void x_launch_hot(const XArgs &a, int32_t n, const XConfig &c, cudaStream_t st, XPersist ps) {
     if (c.warps == 16)
-        x_launch_t<LOB, CPL, 16, 1, U, false, false>(a, n, c.rows_per_cta, st);
+        x_launch_t<LOB, CPL, 16, 1, U, false, false>(a, n, c.rows_per_cta, st, ps);
     else if (c.minb == 3)
-        x_launch_t<LOB, CPL, 8, 3, U, false, false>(a, n, c.rows_per_cta, st);
+        x_launch_t<LOB, CPL, 8, 3, U, false, false>(a, n, c.rows_per_cta, st, ps);
     else
-        x_launch_t<LOB, CPL, 8, 2, U, false, false>(a, n, c.rows_per_cta, st);
+        x_launch_t<LOB, CPL, 8, 2, U, false, false>(a, n, c.rows_per_cta, st, ps);
 }
 
 template <int LOB, int CPL>
-static void x_launch_fmt(const XArgs &a, int32_t n, const XConfig &c, bool in_f32, bool out_f32, cudaStream_t st) {
+static void x_launch_fmt(const XArgs &a, int32_t n, const XConfig &c, bool in_f32, bool out_f32, cudaStream_t st,
+                         XPersist ps) {
     if (!in_f32 && !out_f32) {
         if (c.u == 2)
-            x_launch_hot<LOB, CPL, 2>(a, n, c, st);
+            x_launch_hot<LOB, CPL, 2>(a, n, c, st, ps);
         else
-            x_launch_hot<LOB, CPL, 4>(a, n, c, st);
+            x_launch_hot<LOB, CPL, 4>(a, n, c, st, ps);
         return;
     }
     const int rpc = 64;  // first / last update of a run: float32 rows in or out
@@ -555,17 +602,18 @@ static void x_launch_fmt(const XArgs &a, int32_t n, const XConfig &c, bool in_f3
         x_launch_t<LOB, CPL, 8, 2, 2, false, true>(a, n, rpc, st);
 }
 
-static void x_launch(const XArgs &a, int32_t n, const XConfig &c, bool in_f32, bool out_f32, cudaStream_t st) {
+static void x_launch(const XArgs &a, int32_t n, const XConfig &c, bool in_f32, bool out_f32, cudaStream_t st,
+                     XPersist ps = XPersist()) {
     if (c.lob == 16) {
         if (c.cpl == 8)
-            x_launch_fmt<16, 8>(a, n, c, in_f32, out_f32, st);
+            x_launch_fmt<16, 8>(a, n, c, in_f32, out_f32, st, ps);
         else
-            x_launch_fmt<16, 4>(a, n, c, in_f32, out_f32, st);
+            x_launch_fmt<16, 4>(a, n, c, in_f32, out_f32, st, ps);
     } else {
         if (c.cpl == 8)
-            x_launch_fmt<8, 8>(a, n, c, in_f32, out_f32, st);
+            x_launch_fmt<8, 8>(a, n, c, in_f32, out_f32, st, ps);
         else
-            x_launch_fmt<8, 4>(a, n, c, in_f32, out_f32, st);
+            x_launch_fmt<8, 4>(a, n, c, in_f32, out_f32, st, ps);
     }
 }
 
@@ -635,6 +683,8 @@ int32_t cy2p_propagate_x(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t 
     }
     const bool wide_all = (B % 4 == 0) && (((uintptr_t)d_X0 & 15) == 0) && (!d_Xfinal || ((uintptr_t)d_Xfinal & 15) == 0);
     unsigned char *bufA = (unsigned char *)(ws + w.bufA), *bufB = (unsigned char *)(ws + w.bufB);
+    int32_t *counters = (int32_t *)(ws + w.counters);
+    int64_t launch_no = 0;
     for (int32_t c0 = 0; c0 < B; c0 += w.tile) {
         const int32_t nc = (B - c0 < w.tile) ? B - c0 : w.tile;
         if (d_eps)
@@ -662,7 +712,14 @@ int32_t cy2p_propagate_x(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t 
             a.pi_rows = pi_rows;
             a.eps_acc = d_eps ? eps_acc + 2 * (size_t)it * (size_t)nc * kXEpsCopies : nullptr;
             a.eps_scale = scal;
-            x_launch(a, n, c, first, last, st);
+            XPersist ps;
+            if (c.persist && !first && !last) {
+                const int64_t slot = launch_no++ % kXCounterSlots;
+                if (slot == 0) CY2P_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * kXCounterSlots, st));
+                ps.counter = counters + slot;
+                ps.num_sms = plan->num_sms;
+            }
+            x_launch(a, n, c, first, last, st, ps);
             src = dst;
         }
         if (d_eps) {

@@ -175,3 +175,40 @@ def test_decoders_match_reference_golden(golden, name):
     assert np.array_equal(psi.cpu().numpy(), g["psi"])
     assert np.array_equal(np.array(best, dtype=np.float64), g["best_path"])
     assert isinstance(best[0][-1], int) and isinstance(best[0][0], float)
+
+
+@pytest.mark.parametrize("S,L,restricted,two_pass", [(10, 4, False, 0), (16, 4, False, 0), (10, 4, True, 1), (5, 3, True, 1)])
+def test_tensor_core_gradients_match_ffma_path(monkeypatch, S, L, restricted, two_pass):
+    """The two data-term gradients on the tensor cores (mma.sync TF32 with the 3xTF32 split, csrc/fhmm.cu
+    fhmm_dE_mma / fhmm_dG_mma) against the FFMA slices of the same two-pass path, and — for small emission matrices —
+    against the fused single-pass kernel."""
+    from cy2path_b200 import _lib
+    from cy2path_b200.models import FHMM
+    from cy2path_b200.sampling import get_plan
+    from cy2path_b200.synth import knn_velocity_tpm
+
+    N, I = 3000, 130
+    g = knn_velocity_tpm(N, k=12, seed=33)
+    plan = get_plan(g["T"])
+    x0 = torch.tensor((g["root_cells"] / g["root_cells"].sum()).astype(np.float32)).cuda()
+    D = _lib.propagate(plan, x0, I, history_stride=1, want_final=False)["history"].contiguous()
+    torch.manual_seed(11)
+    m = FHMM(S, L, N, I, restricted=restricted, use_gpu=True)
+    params = [p.data for p in m.parameters()]
+    wts = (1.0, 0.1, 0.1, 0.05)
+
+    def run(mma, tp):
+        monkeypatch.setenv("CY2P_FHMM_MMA", str(mma))
+        monkeypatch.setenv("CY2P_FHMM_TWO_PASS", str(tp))
+        terms, grads, _ = _lib.fhmm_loss_grad(plan, *params, D, restricted, wts)
+        return terms.cpu().numpy().copy(), [x.cpu().numpy().copy() for x in grads]
+
+    t_mma, g_mma = run(1, two_pass)
+    t_ffma, g_ffma = run(0, two_pass)
+    t_fused, g_fused = run(0, 0) if two_pass else (t_ffma, g_ffma)
+    assert np.abs(t_mma - t_ffma).max() <= 1e-6 * max(1.0, np.abs(t_ffma).max())
+    for a, b, c in zip(g_mma, g_ffma, g_fused):
+        scale = np.abs(b).max()
+        # 3xTF32 keeps ~21 bits per factor and the tensor pipe's fp32 accumulation truncates: measured 5e-6 of max|g|
+        assert np.abs(a - b).max() <= 1e-7 + 2e-5 * scale
+        assert np.abs(a - c).max() <= 1e-7 + 2e-5 * scale

@@ -61,8 +61,9 @@ def test_small_cases_match_oracle(B, iters, tail):
     assert _rel_l1_cols(g64, ref) <= (iters * 2e-11 if tail == 16 else iters * 5e-9)
 
 
-@pytest.mark.parametrize("cpl,warps,minb,u", [(4, 8, 2, 2), (4, 8, 3, 4), (4, 16, 1, 4), (8, 8, 3, 2), (8, 16, 1, 2)])
-def test_kernel_shape_variants_agree(monkeypatch, cpl, warps, minb, u):
+@pytest.mark.parametrize("cpl,warps,minb,u,persist", [(4, 8, 2, 2, 0), (4, 8, 3, 4, 1), (4, 16, 1, 4, 0), (8, 8, 3, 2, 0),
+                                                      (8, 16, 1, 2, 1), (8, 8, 2, 4, 1)])
+def test_kernel_shape_variants_agree(monkeypatch, cpl, warps, minb, u, persist):
     """The tuning variants (columns per lane, warps per CTA) walk the same rows in the same order: identical bits."""
     import torch
 
@@ -79,6 +80,7 @@ def test_kernel_shape_variants_agree(monkeypatch, cpl, warps, minb, u):
     monkeypatch.setenv("CY2PX_WARPS", str(warps))
     monkeypatch.setenv("CY2PX_MINB", str(minb))
     monkeypatch.setenv("CY2PX_U", str(u))
+    monkeypatch.setenv("CY2PX_PERSIST", str(persist))
     for tail in (16, 8):
         ref = base if tail == 16 else None
         got = _lib.propagate_x(plan, X0, 30, stationary=stat, want_eps=True, tail_bits=tail)
