@@ -84,6 +84,9 @@ struct cy2p_plan {
     int32_t *d_blk_usrc = nullptr;         // distinct sources (permuted positions, ascending) of each block
     cy2p::Pair *d_r_pairs_lp = nullptr;    // d_r_pairs_pp with src replaced by the index in the block's list
     double blk_reuse = 0.0;                // stored entries / distinct sources, averaged over the blocks
+    // side stream + events of cy2p_fhmm_loss_grad (fhmm.cu): the node-level passes run beside the pass over D
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t side_events[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace cy2p {

@@ -2116,10 +2116,8 @@ int32_t run_emission(int K, int N, const float *theta_E, const FhmmWs &w, char *
     return CY2P_OK;
 }
 
-int32_t run_forward(int S, int L, int Le, int N, int I, int restricted, const float *theta_pi, const float *theta_w,
-                    const float *theta_E, const float *theta_A, const FhmmWs &w, char *ws, cudaStream_t st) {
-    int32_t rc = run_emission(S * Le, N, theta_E, w, ws, st);
-    if (rc) return rc;
+int32_t run_small_forward(int S, int L, int I, int restricted, const float *theta_pi, const float *theta_w,
+                          const float *theta_A, const FhmmWs &w, char *ws, cudaStream_t st) {
     if (w.smem_fwd > 220 * 1024 || w.smem_bwd > 220 * 1024) {
         set_error("model too large for the one-CTA recurrence kernels (S=%d, L=%d, I=%d)", S, L, I);
         return CY2P_ERR_INVALID_ARG;
@@ -2132,6 +2130,13 @@ int32_t run_forward(int S, int L, int Le, int N, int I, int restricted, const fl
                                                    (double *)(ws + w.Apow));
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
+}
+
+int32_t run_forward(int S, int L, int Le, int N, int I, int restricted, const float *theta_pi, const float *theta_w,
+                    const float *theta_E, const float *theta_A, const FhmmWs &w, char *ws, cudaStream_t st) {
+    int32_t rc = run_emission(S * Le, N, theta_E, w, ws, st);
+    if (rc) return rc;
+    return run_small_forward(S, L, I, restricted, theta_pi, theta_w, theta_A, w, ws, st);
 }
 
 // ---- LSSM: the FHMM work space (for the node / data passes with L lineages) plus the single-chain pieces
@@ -2410,37 +2415,66 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
 
     CY2P_CUDA(cudaMemsetAsync(ws + w.gG, 0, sizeof(float) * (size_t)I * K, st));
     CY2P_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * sc.total, st));
-    rc = run_forward(S, L, Le, N, I, restricted, theta_pi, theta_w, theta_E, theta_A, w, ws, st);
+    // Two streams (CY2P_FHMM_OVERLAP=0: one). The epoch's dependency graph has two independent arms after the memsets:
+    //   main: emission softmax -> [wait small_forward] -> pass over D (P / r, dlogE, dG on the tensor cores)
+    //   side: small_forward (one CTA, ~65 us of dependent steps) -> [wait logE] -> node-level conditionals, their
+    //         products with T (K1 with B = S + L), regulariser sums, log-likelihood  (~150 us of small kernels)
+    // and they join before the regulariser gradients (which add the dlogE slices) and the backward recurrences.
+    cudaStream_t s2 = st;
+    cudaEvent_t *ev = plan->side_events;
+    if (env_flag("CY2P_FHMM_OVERLAP", 1)) {
+        if (!plan->side_stream) {
+            CY2P_CUDA(cudaStreamCreateWithFlags(&plan->side_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 4; ++i) CY2P_CUDA(cudaEventCreateWithFlags(&plan->side_events[i], cudaEventDisableTiming));
+        }
+        s2 = plan->side_stream;
+        CY2P_CUDA(cudaEventRecord(ev[0], st));  // fork: the memsets and the caller's earlier work
+        CY2P_CUDA(cudaStreamWaitEvent(s2, ev[0], 0));
+    }
+    const bool two = s2 != st;
+    rc = run_emission(K, N, theta_E, w, ws, st);
     if (rc) return rc;
-    // pass over D
+    if (two) CY2P_CUDA(cudaEventRecord(ev[1], st));  // logE ready
+    rc = run_small_forward(S, L, I, restricted, theta_pi, theta_w, theta_A, w, ws, s2);
+    if (rc) return rc;
+    if (two) {
+        CY2P_CUDA(cudaEventRecord(ev[2], s2));  // G, aux, small ready
+        CY2P_CUDA(cudaStreamWaitEvent(st, ev[2], 0));
+        CY2P_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
+    }
+    // pass over D (main stream)
     dispatch_data_pass(N, I, K, w, ws, logE, (const float *)(ws + w.G), d_D, nullptr, (float *)(ws + w.split),
                        (float *)(ws + w.gG), scal + sc.div, st);
-    // node-level conditionals and their products with T
+    // node-level conditionals and their products with T (side stream)
     const unsigned gN = (unsigned)((N + 127) / 128);
     count_launch();
-    fhmm_node_pass_a<<<gN, 128, 0, st>>>(S, L, Le, N, logE, (const float *)(ws + w.aux), X1, X2);
-    rc = cy2p_propagate_rows(plan, X1, Y1, S + L, 0, N, stream);  // [P(n|s) | P(n|l)] . T   (trainer.py:175,190)
+    fhmm_node_pass_a<<<gN, 128, 0, s2>>>(S, L, Le, N, logE, (const float *)(ws + w.aux), X1, X2);
+    rc = cy2p_propagate_rows(plan, X1, Y1, S + L, 0, N, (void *)s2);  // [P(n|s) | P(n|l)] . T   (trainer.py:175,190)
     if (rc) return rc;
     count_launch();
-    csr_times_small<<<(unsigned)(((int64_t)N * L + 255) / 256), 256, 0, st>>>(N, L, plan->d_indptr, plan->d_indices,
+    csr_times_small<<<(unsigned)(((int64_t)N * L + 255) / 256), 256, 0, s2>>>(N, L, plan->d_indptr, plan->d_indices,
                                                                              plan->d_data, X2, TP);
     count_launch();
-    fhmm_node_pass_b<<<gN, 128, 0, st>>>(S, L, Le, N, logE, (const float *)(ws + w.aux), X1, X2, Y1, scal, K);
+    fhmm_node_pass_b<<<gN, 128, 0, s2>>>(S, L, Le, N, logE, (const float *)(ws + w.aux), X1, X2, Y1, scal, K);
+    // log-likelihood (side stream)
+    count_launch();
+    fhmm_ll_nodes<<<(unsigned)((N + 255) / 256), 256, 0, s2>>>(S, L, Le, N, I, logE, (const double *)(ws + w.row_lse),
+                                                               (double *)(ws + w.llv));
+    const int nparts = (N + 255) / 256;
+    count_launch();
+    lse_partials<<<nparts, 256, 0, s2>>>(N, (const double *)(ws + w.llv), (double2 *)(ws + w.llpart));
+    count_launch();
+    lse_combine<<<1, 256, 0, s2>>>(nparts, (const double2 *)(ws + w.llpart), scal + sc.ll);
+    if (two) {
+        CY2P_CUDA(cudaEventRecord(ev[3], s2));  // join
+        CY2P_CUDA(cudaStreamWaitEvent(st, ev[3], 0));
+    }
     count_launch();
     fhmm_node_pass_c<<<gN, 128, 0, st>>>(S, L, Le, N, K, w.nsplit, logE, (const float *)(ws + w.aux), X1, X2, Y1, TP,
                                          (const float *)(ws + w.split), scal, w_excl, w_orth, w_tpm, d_gE);
     count_launch();
     fhmm_emission_grad_finish<<<(unsigned)(((int64_t)K * N + 255) / 256), 256, 0, st>>>(N, K, logE, scal + sc.rowsum,
                                                                                        d_gE);
-    // log-likelihood
-    count_launch();
-    fhmm_ll_nodes<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(S, L, Le, N, I, logE, (const double *)(ws + w.row_lse),
-                                                               (double *)(ws + w.llv));
-    const int nparts = (N + 255) / 256;
-    count_launch();
-    lse_partials<<<nparts, 256, 0, st>>>(N, (const double *)(ws + w.llv), (double2 *)(ws + w.llpart));
-    count_launch();
-    lse_combine<<<1, 256, 0, st>>>(nparts, (const double2 *)(ws + w.llpart), scal + sc.ll);
     // small backward
     const int NB = (I + w.P - 1) / w.P;
     CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_local));

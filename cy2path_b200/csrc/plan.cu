@@ -172,6 +172,9 @@ static void plan_free(cy2p_plan *p) {
     cudaFree(p->d_blk_uptr);
     cudaFree(p->d_blk_usrc);
     cudaFree(p->d_r_pairs_lp);
+    if (p->side_stream) cudaStreamDestroy(p->side_stream);
+    for (cudaEvent_t e : p->side_events)
+        if (e) cudaEventDestroy(e);
     cudaFree(p->d_t_pairsD);
     cudaFree(p->d_r_pairsD_pp);
     cudaFree(p->d_r_pairsD_op);

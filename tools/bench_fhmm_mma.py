@@ -11,7 +11,11 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 CASES = {
-    "restricted_fused_ffma2": (True, {"CY2P_FHMM_TWO_PASS": "0", "CY2P_FHMM_MMA": "0"}),
+    "restricted_mma_overlap": (True, {"CY2P_FHMM_TWO_PASS": "1", "CY2P_FHMM_MMA": "1", "CY2P_FHMM_OVERLAP": "1"}),
+    "restricted_mma_serial": (True, {"CY2P_FHMM_TWO_PASS": "1", "CY2P_FHMM_MMA": "1", "CY2P_FHMM_OVERLAP": "0"}),
+    "unrestricted_mma_overlap": (False, {"CY2P_FHMM_TWO_PASS": "1", "CY2P_FHMM_MMA": "1", "CY2P_FHMM_OVERLAP": "1"}),
+    "unrestricted_mma_serial": (False, {"CY2P_FHMM_TWO_PASS": "1", "CY2P_FHMM_MMA": "1", "CY2P_FHMM_OVERLAP": "0"}),
+    "restricted_fused_ffma2": (True, {"CY2P_FHMM_TWO_PASS": "0", "CY2P_FHMM_MMA": "0", "CY2P_FHMM_OVERLAP": "0"}),
     "restricted_twopass_ffma": (True, {"CY2P_FHMM_TWO_PASS": "1", "CY2P_FHMM_MMA": "0"}),
     "restricted_twopass_mma": (True, {"CY2P_FHMM_TWO_PASS": "1", "CY2P_FHMM_MMA": "1"}),
     "unrestricted_twopass_ffma": (False, {"CY2P_FHMM_TWO_PASS": "0", "CY2P_FHMM_MMA": "0"}),
