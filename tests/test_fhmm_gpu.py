@@ -2,7 +2,9 @@
 
 Parity bar: forward outputs and loss terms within 1e-5 max-abs; log-likelihood within 1e-6 relative
 (its magnitude ~ I*log N is beyond fp32's 1e-5 absolute resolution); gradients
-within 1e-5 + 1e-3*max|g| of the reference's autograd.
+within 1e-5 + 1e-4*max|g| of the reference's autograd (measured: <= 1.4e-5 * max|g| over the nine golden cases,
+profiles/tolerance_probe_r02.jsonl). Decoder outputs are log-probabilities of magnitude ~100, where one fp32 ulp is
+7.6e-6: they are held to 1e-5 + 1e-6*max|ref| (measured <= 5.3e-5 at magnitude 107).
 """
 import numpy as np
 import pytest
@@ -70,7 +72,7 @@ def test_loss_terms_and_gradients_match_reference_golden(golden, name):
     for gq, nme in zip(grads, NAMES):
         rg = g["grad_" + nme]
         assert gq.shape == rg.shape
-        assert np.abs(gq.cpu().numpy() - rg).max() <= 1e-5 + 1e-3 * np.abs(rg).max(), nme
+        assert np.abs(gq.cpu().numpy() - rg).max() <= 1e-5 + 1e-4 * np.abs(rg).max(), nme
 
 
 @pytest.mark.parametrize("kind", ["fhmm", "lssm", "nssm"])
@@ -112,7 +114,7 @@ def test_mid_size_vs_oracle_autograd(S, L, restricted, N, I, kind):
     assert abs(t["log_likelihood"] - ll) <= 2e-6 * abs(ll) + 1e-5
     for gq, r, nme in zip(grads, th, NAMES):
         rg = r.grad.numpy()
-        assert np.abs(gq.cpu().numpy() - rg).max() <= 1e-5 + 2e-3 * np.abs(rg).max(), nme
+        assert np.abs(gq.cpu().numpy() - rg).max() <= 1e-5 + 2e-4 * np.abs(rg).max(), nme
     pred = m.forward_model(want_joint=False)[0]
     assert np.abs(pred.cpu().numpy() - ref["pred"].detach().numpy()).max() <= 2e-5
 
@@ -171,7 +173,7 @@ def test_decoders_match_reference_golden(golden, name):
                      (lmax, "log_max")):
         ref = g[key]
         assert got.shape == ref.shape, key
-        assert np.abs(got.cpu().numpy() - ref).max() <= 2e-4 + 1e-5 * np.abs(ref).max(), key
+        assert np.abs(got.cpu().numpy() - ref).max() <= 1e-5 + 1e-6 * np.abs(ref).max(), key
     assert np.array_equal(psi.cpu().numpy(), g["psi"])
     assert np.array_equal(np.array(best, dtype=np.float64), g["best_path"])
     assert isinstance(best[0][-1], int) and isinstance(best[0][0], float)
