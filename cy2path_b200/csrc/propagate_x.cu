@@ -21,6 +21,7 @@
 // eps (sampling.py:44-45) is deterministic here: per-thread float64 partial sums over the thread's rows in a fixed
 // order, then 64-bit FIXED-POINT integer atomics (integer addition is associative, so the order in which warps and
 // CTAs arrive cannot change a bit of the result) — see eps_scale_kernel for the scale.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -28,6 +29,8 @@
 #include "common.cuh"
 
 namespace cy2p {
+
+namespace cgx = cooperative_groups;
 
 constexpr int kXEpsCopies = 4;  // spread of the global integer accumulators (same-address atomics serialise in L2)
 
@@ -371,6 +374,44 @@ spmm_gather_x_persist(int32_t n_rows, int32_t rows_per_item, int32_t nslabs, int
     }
 }
 
+// Persistent MULTI-ITERATION variant (the shape the north_star names: one launch carries a column tile through many
+// updates, the ping-pong iterate sized to stay in L2): a cooperative grid of num_SMs x MINB CTAs, a work counter per
+// update, grid.sync() between updates. Opt-in (CY2PX_MULTI=1): measured against the default in
+// profiles/k1x_sweep_multi_r02.jsonl — the update is bound by the L2 -> SM path either way, so keeping HBM out of it
+// (DRAM traffic -> 0) does not shorten it, and the narrow tile an L2-resident iterate needs (128 columns at 50k cells)
+// leaves the grid barrier and the tail of every update exposed.
+template <int LOB, int CPL, int WARPS, int MINB, int U, bool EPS>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+spmm_gather_x_multi(int32_t n_rows, int32_t rows_per_item, int32_t nslabs, int32_t n_updates, int32_t *__restrict__ counters,
+                    unsigned char *bufA, unsigned char *bufB, int32_t first_src_is_A, size_t eps_stride, XArgs a) {
+    cgx::grid_group grid = cgx::this_grid();
+    __shared__ unsigned long long s_acc[2][CPL][32];
+    __shared__ unsigned s_done;
+    __shared__ int32_t s_item;
+    const int32_t nrg = (n_rows + rows_per_item - 1) / rows_per_item;
+    const int32_t total = nrg * nslabs;
+    for (int32_t it = 0; it < n_updates; ++it) {
+        const bool src_is_A = ((it & 1) == 0) == (first_src_is_A != 0);
+        XArgs b = a;
+        b.xin = src_is_A ? bufA : bufB;
+        b.xout = src_is_A ? bufB : bufA;
+        if (EPS) b.eps_acc = a.eps_acc + (size_t)it * eps_stride;
+        for (;;) {
+            if (threadIdx.x == 0) s_item = atomicAdd(counters + it, 1);
+            __syncthreads();
+            const int32_t item = s_item;
+            if (item >= total) break;
+            const int32_t slab = item / nrg, rg = item % nrg;
+            const int32_t row0 = rg * rows_per_item;
+            gather_block_x<LOB, CPL, WARPS, U, false, false, EPS>(b, row0, min(row0 + rows_per_item, n_rows), slab,
+                                                                   rg % kXEpsCopies, s_acc, &s_done);
+            __syncthreads();
+        }
+        __threadfence();
+        grid.sync();  // every row of this update is written (and visible) before anyone gathers from it
+    }
+}
+
 // ---- small kernels ----------------------------------------------------------------------------------------------
 __global__ void widen_pairs_kernel(int64_t nnz, const Pair *__restrict__ in, PairD *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -690,6 +731,8 @@ int32_t cy2p_propagate_x(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t 
         if (d_eps)
             CY2P_CUDA(cudaMemsetAsync(eps_acc, 0, sizeof(unsigned long long) * 2 * (size_t)iters * (size_t)nc * kXEpsCopies, st));
         unsigned char *src = nullptr;
+        const int multi_env = x_env_int("CY2PX_MULTI", 0);
+        const bool multi = multi_env && iters >= 4 && c.cpl == 4 && c.warps == 8 && iters - 2 <= kXCounterSlots;
         for (int32_t it = 0; it < iters; ++it) {
             const bool first = it == 0, last = it + 1 == iters;
             XArgs a;
@@ -712,6 +755,26 @@ int32_t cy2p_propagate_x(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t 
             a.pi_rows = pi_rows;
             a.eps_acc = d_eps ? eps_acc + 2 * (size_t)it * (size_t)nc * kXEpsCopies : nullptr;
             a.eps_scale = scal;
+            if (multi && it == 1) {  // updates 1 .. iters-2 in ONE cooperative launch
+                const int32_t n_upd = iters - 2;
+                CY2P_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * kXCounterSlots, st));
+                int32_t n_ = n, rpi = c.rows_per_cta, nslabs = (nc + 32 * 4 - 1) / (32 * 4), srcA = (src == bufA) ? 1 : 0;
+                size_t eps_stride = 2 * (size_t)nc * kXEpsCopies;
+                void *args[] = {&n_, &rpi, &nslabs, (void *)&n_upd, &counters, &bufA, &bufB, &srcA, &eps_stride, &a};
+                const dim3 grid((unsigned)(plan->num_sms * 2));
+                count_launch();
+                cudaError_t le;
+                if (c.lob == 16)
+                    le = d_eps ? cudaLaunchCooperativeKernel((void *)spmm_gather_x_multi<16, 4, 8, 2, 4, true>, grid, dim3(256), args, 0, st)
+                               : cudaLaunchCooperativeKernel((void *)spmm_gather_x_multi<16, 4, 8, 2, 4, false>, grid, dim3(256), args, 0, st);
+                else
+                    le = d_eps ? cudaLaunchCooperativeKernel((void *)spmm_gather_x_multi<8, 4, 8, 2, 4, true>, grid, dim3(256), args, 0, st)
+                               : cudaLaunchCooperativeKernel((void *)spmm_gather_x_multi<8, 4, 8, 2, 4, false>, grid, dim3(256), args, 0, st);
+                CY2P_CUDA(le);
+                if (n_upd & 1) src = dst;  // an odd number of updates ends in the other buffer
+                it += n_upd - 1;
+                continue;
+            }
             XPersist ps;
             if (c.persist && !first && !last) {
                 const int64_t slot = launch_no++ % kXCounterSlots;

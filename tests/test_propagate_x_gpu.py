@@ -94,6 +94,31 @@ def test_kernel_shape_variants_agree(monkeypatch, cpl, warps, minb, u, persist):
             assert _rel_l1_cols(got["final"].cpu().numpy(), ref8) <= REL_L1
 
 
+def test_multi_iteration_persistent_variant_agrees(monkeypatch):
+    """CY2PX_MULTI=1: all middle updates of a column tile in one cooperative launch (grid barrier per update)."""
+    import torch
+
+    from cy2path_b200 import _lib
+    from cy2path_b200.synth import batched_starts, knn_velocity_tpm, stationary_by_power
+
+    g = knn_velocity_tpm(3000, k=15, seed=11)
+    T = g["T"]
+    plan = _lib.Plan(T)
+    X0 = torch.from_numpy(batched_starts(T, 300, seed=1)).cuda()
+    stat = stationary_by_power(T, 30)
+    for iters in (30, 31, 4):
+        base = _lib.propagate_x(plan, X0, iters, stationary=stat, want_eps=True)
+        monkeypatch.setenv("CY2PX_MULTI", "1")
+        monkeypatch.setenv("CY2PX_CPL", "4")
+        monkeypatch.setenv("CY2P_TILE", "128")
+        got = _lib.propagate_x(plan, X0, iters, stationary=stat, want_eps=True)
+        monkeypatch.delenv("CY2PX_MULTI")
+        monkeypatch.delenv("CY2PX_CPL")
+        monkeypatch.delenv("CY2P_TILE")
+        assert torch.equal(got["final"], base["final"])
+        assert float((got["eps"] - base["eps"]).abs().max()) <= 1e-13
+
+
 def test_long_run_2000_iterations_all_formats():
     """2,000 updates of 8 starts on the config-1 graph (the horizon of BASELINE configs 2 / 4)."""
     import torch

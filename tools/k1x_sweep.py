@@ -28,6 +28,9 @@ for _tail, _nm in ((16, "f48"), (8, "f40")):
 for _cpl, _w, _mb, _r in ((8, 8, 2, 64), (8, 8, 2, 128), (8, 8, 2, 256), (8, 16, 1, 128), (8, 16, 1, 256), (8, 16, 1, 512),
                          (4, 8, 3, 128), (4, 16, 1, 256)):
     CONFIGS["f48_persist_c%d_w%d_m%d_r%d" % (_cpl, _w, _mb, _r)] = _x(16, cpl=_cpl, warps=_w, minb=_mb, u=4, persist=1, rows=_r)
+for _t in (128, 256, 512, 2048):
+    CONFIGS["f48_multi_c4_t%d" % _t] = ("x", 16, {"CY2PX_MULTI": "1", "CY2PX_CPL": "4", "CY2PX_MINB": "2", "CY2P_TILE": str(_t)})
+    CONFIGS["f48_plain_c4_t%d" % _t] = ("x", 16, {"CY2PX_CPL": "4", "CY2PX_MINB": "2", "CY2P_TILE": str(_t)})
 CONFIGS["f48_default"] = ("x", 16, {})
 CONFIGS["f40_default"] = ("x", 8, {})
 for _t in (128, 512, 1024):
@@ -61,7 +64,7 @@ def main():
     out = open(a.out, "a") if a.out else None
     for name in names:
         kind, tail, env = CONFIGS[name]
-        saved = {k: os.environ.get(k) for k in ("CY2PX_CPL", "CY2PX_WARPS", "CY2PX_ROWS", "CY2P_TILE", "CY2PX_MINB", "CY2PX_U", "CY2PX_PERSIST")}
+        saved = {k: os.environ.get(k) for k in ("CY2PX_CPL", "CY2PX_WARPS", "CY2PX_ROWS", "CY2P_TILE", "CY2PX_MINB", "CY2PX_U", "CY2PX_PERSIST", "CY2PX_MULTI")}
         for k in saved:
             os.environ.pop(k, None)
         os.environ.update(env)
