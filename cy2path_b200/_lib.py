@@ -211,6 +211,15 @@ class Plan:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         indptr = np.ascontiguousarray(T.indptr, dtype=np.int32)
         indices = np.ascontiguousarray(T.indices, dtype=np.int32)
+        if np.asarray(T.data).dtype == np.float64:
+            import warnings
+
+            data32 = np.asarray(T.data, dtype=np.float32)
+            if not np.array_equal(data32.astype(np.float64), T.data):
+                warnings.warn("the transition matrix holds float64 values that are not exactly representable in float32; "
+                              "the device plan stores float32 (scvelo's dtype): results follow the ROUNDED matrix, which "
+                              "leaves the reference's float64 product by ~2e-9 relative L1 per iteration "
+                              "(INTEGRATION.md §1). Pass T.astype(np.float32) to silence this.", stacklevel=3)
         data = np.ascontiguousarray(T.data, dtype=np.float32)
         handle = _vp(0)
         with torch.cuda.device(self.device):
