@@ -21,7 +21,7 @@ SYMBOLS = [
     "cy2p_abi_version", "cy2p_last_error", "cy2p_launch_count", "cy2p_plan_create", "cy2p_plan_create_host", "cy2p_plan_destroy",
     "cy2p_plan_info", "cy2p_propagate_ws_bytes", "cy2p_propagate_column_tile", "cy2p_propagate", "cy2p_propagate_rows",
     "cy2p_propagate_f64_ws_bytes", "cy2p_propagate_f64", "cy2p_propagate_rows_f64", "cy2p_plan_order",
-    "cy2p_propagate_x_ws_bytes", "cy2p_propagate_x_column_tile", "cy2p_propagate_x", "cy2p_order_host", "cy2p_xbarrier",
+    "cy2p_propagate_x_ws_bytes", "cy2p_propagate_x_column_tile", "cy2p_propagate_x", "cy2p_order_host", "cy2p_xbarrier", "cy2p_propagate_rows_persist", "cy2p_propagate_rows_persist_f64",
     "cy2p_propagate_rows_ordered", "cy2p_propagate_rows_ordered_f64", "cy2p_propagate_rows_allgather",
     "cy2p_propagate_rows_allgather_f64", "cy2p_propagate_rows_push", "cy2p_propagate_rows_push_f64",
     "cy2p_enable_peer_access", "cy2p_cdf_build",
@@ -71,6 +71,8 @@ def load():
     lib.cy2p_propagate_x_column_tile.argtypes = [_vp, _i32, _i32]
     lib.cy2p_order_host.argtypes = [_i32, _i64, _vp, _vp, _i32, _vp]
     lib.cy2p_xbarrier.argtypes = [_vp, _vp, _vp, _i32, _i32, _vp, _vp]
+    lib.cy2p_propagate_rows_persist.argtypes = [_vp, _vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]
+    lib.cy2p_propagate_rows_persist_f64.argtypes = lib.cy2p_propagate_rows_persist.argtypes
     lib.cy2p_propagate_x.argtypes = [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]
     lib.cy2p_propagate_rows_ordered.argtypes = lib.cy2p_propagate_rows.argtypes
     lib.cy2p_propagate_rows_ordered_f64.argtypes = lib.cy2p_propagate_rows.argtypes

@@ -665,6 +665,93 @@ spmv_rows(int32_t row_begin, int32_t row_end, const int32_t *__restrict__ t_indp
     }
 }
 
+// Persistent single-start update of a row range for the row-partitioned run (config 5, B == 1): ALL updates in one
+// cooperative launch. Per update: the rank's rows (8 lanes per row, as spmv_rows) are formed from its full-size
+// iterate and stored into the next-iterate buffers of the ranks that gather them (own HBM + NVLink peer stores, per-row
+// masks); then grid barrier -> cross-GPU flag exchange by one CTA (every rank writes its epoch into its slot of every
+// rank's flag array and waits for all slots of its own: the protocol of cy2p_xbarrier, propagate_x.cu) -> grid barrier.
+// No kernel launch and no host round trip per update: at 10^6 cells on 8 GPUs an update is ~6 us of gathers.
+// The iterate is read with ordinary L1-cached loads (ld.global.ca — in the locality order neighbouring rows share
+// sectors, and the L2-only loads of a first version ran the gather 2x slower): rows written by peers and by this rank one
+// update ago cannot be served from a stale L1 line because every CTA passes the gpu-scope fences of grid.sync() after
+// the flag exchange (a gpu-scope fence invalidates the SM's L1), and the peers' rows are in this GPU's L2 before their flag
+// (fence.sys on the writer's side). A barrier that is not reached within ~2 s sets *d_error and stops waiting for good.
+__device__ __forceinline__ float ld_ca(const float *p) {
+    float v;
+    asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_ca(const double *p) {
+    double v;
+    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+spmv_rows_persist(int32_t row_begin, int32_t row_end, const int32_t *__restrict__ t_indptr,
+                  const Pair *__restrict__ pairs, T *const *__restrict__ peer_buf0, T *const *__restrict__ peer_buf1,
+                  const uint32_t *__restrict__ peer_mask, int32_t rank, int32_t world, int32_t iters,
+                  int32_t *const *__restrict__ peer_flags, volatile int32_t *my_flags, int32_t *epoch_counter,
+                  int32_t *d_error) {
+    cg::grid_group grid = cg::this_grid();
+    constexpr int G = 8;
+    const int lane = threadIdx.x & 31, gl = lane % G;
+    const int32_t epoch0 = *(volatile int32_t *)epoch_counter;
+    const int32_t rows_per_pass = gridDim.x * (blockDim.x / G);
+    bool dead = false;
+    for (int32_t it = 0; it < iters; ++it) {
+        T *const *src_tab = (it & 1) ? peer_buf1 : peer_buf0;
+        T *const *dst_tab = (it & 1) ? peer_buf0 : peer_buf1;
+        const T *x = src_tab[rank];
+        // the loop bound is WARP-uniform (a warp covers 32 / G consecutive rows): all 32 lanes reach the shuffles
+        for (int32_t rw = row_begin + (int32_t)(blockIdx.x * (blockDim.x / G) + (threadIdx.x >> 5) * (32 / G)); rw < row_end;
+             rw += rows_per_pass) {
+            const int32_t r = rw + lane / G;
+            const bool ok = r < row_end;
+            const int32_t beg = ok ? __ldg(t_indptr + r) : 0, end = ok ? __ldg(t_indptr + r + 1) : 0;
+            T acc = (T)0;
+            for (int32_t p0 = beg + gl; p0 < end; p0 += 4 * G) {
+                Pair e[4];
+                T xv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int32_t p = p0 + k * G;
+                    e[k] = p < end ? pairs[p] : Pair{0, 0.f};
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xv[k] = (p0 + k * G < end) ? ld_ca(x + e[k].src) : (T)0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc = fma((T)e[k].val, xv[k], acc);
+            }
+#pragma unroll
+            for (int o = G / 2; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (ok) {
+                const uint32_t want = peer_mask ? __ldg(peer_mask + r) : 0xffffffffu;
+                for (int32_t g = gl; g < world; g += G)
+                    if ((want >> (g & 31)) & 1u) dst_tab[g][r] = acc;
+            }
+        }
+        __threadfence_system();
+        grid.sync();
+        if (blockIdx.x == 0 && (int)threadIdx.x < world && !dead) {
+            const int32_t epoch = epoch0 + it + 1;
+            *(volatile int32_t *)(peer_flags[threadIdx.x] + rank) = epoch;
+            const long long t0 = clock64();
+            while (my_flags[threadIdx.x] - epoch < 0) {
+                if (clock64() - t0 > 4000000000LL || *(volatile int32_t *)d_error) {
+                    atomicExch(d_error, 1);
+                    dead = true;
+                    break;
+                }
+            }
+            __threadfence_system();
+        }
+        grid.sync();
+        __threadfence();  // (explicit: the L1 of this SM holds nothing older than the exchange)
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *epoch_counter = epoch0 + iters;
+}
+
 // pi_rows[r] = (T) stationary[dest_ids ? dest_ids[r] : r]: the stationary vector in the order the rows are walked
 template <typename T>
 __global__ void pi_rows_kernel(int32_t n, const double *__restrict__ stationary, const int32_t *__restrict__ dest_ids,
@@ -1179,6 +1266,33 @@ static int32_t propagate_rows_ordered_impl(cy2p_plan *plan, const T *d_Xp, T *d_
     return CY2P_OK;
 }
 
+template <typename T>
+static int32_t rows_persist_impl(cy2p_plan *plan, void *const *d_peer_buf0, void *const *d_peer_buf1, int32_t world,
+                                 int32_t rank, const uint32_t *d_row_peers, int32_t q_begin, int32_t q_end, int32_t iters,
+                                 void *const *d_peer_flags, int32_t *d_my_flags, int32_t *d_epoch_counter,
+                                 int32_t *d_error, void *stream) {
+    CY2P_REQUIRE(plan && d_peer_buf0 && d_peer_buf1 && d_peer_flags && d_my_flags && d_epoch_counter && d_error, "null pointer");
+    CY2P_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world, "1 <= world <= 32 and 0 <= rank < world required");
+    CY2P_REQUIRE(q_begin >= 0 && q_end <= plan->n && q_begin <= q_end && iters >= 0, "bad row range / iters");
+    cudaStream_t st = (cudaStream_t)stream;
+    CY2P_CUDA(cudaSetDevice(plan->device));
+    if (iters == 0) return CY2P_OK;
+    const bool reord = plan->reorder_state == 1;
+    const int32_t *ip = reord ? plan->d_r_indptr : plan->d_t_indptr;
+    const Pair *pr = reord ? plan->d_r_pairs_pp : plan->d_t_pairs;
+    int per_sm = 0;
+    CY2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_rows_persist<T>, 256, 0));
+    int grid = plan->num_sms * (per_sm > 4 ? 4 : per_sm);
+    const int need = (q_end - q_begin + 31) / 32;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    void *args[] = {&q_begin, &q_end, &ip, &pr, &d_peer_buf0, &d_peer_buf1, &d_row_peers, &rank, &world, &iters,
+                    &d_peer_flags, &d_my_flags, &d_epoch_counter, &d_error};
+    count_launch();
+    CY2P_CUDA(cudaLaunchCooperativeKernel((void *)spmv_rows_persist<T>, dim3(grid), dim3(256), args, 0, st));
+    return CY2P_OK;
+}
+
 __global__ void iota_kernel(int32_t n, int32_t *out) {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = i;
@@ -1237,6 +1351,22 @@ int32_t cy2p_propagate_rows_push_f64(cy2p_plan *plan, const double *d_Xp, void *
                                      void *stream) {
     return propagate_rows_ordered_impl<double>(plan, d_Xp, nullptr, B, q_begin, q_end, stream, d_peer_out, npeers,
                                                d_row_peers);
+}
+
+int32_t cy2p_propagate_rows_persist(cy2p_plan *plan, void *const *d_peer_buf0, void *const *d_peer_buf1, int32_t world,
+                                    int32_t rank, const uint32_t *d_row_peers, int32_t q_begin, int32_t q_end,
+                                    int32_t iters, void *const *d_peer_flags, int32_t *d_my_flags,
+                                    int32_t *d_epoch_counter, int32_t *d_error, void *stream) {
+    return rows_persist_impl<float>(plan, d_peer_buf0, d_peer_buf1, world, rank, d_row_peers, q_begin, q_end, iters,
+                                    d_peer_flags, d_my_flags, d_epoch_counter, d_error, stream);
+}
+
+int32_t cy2p_propagate_rows_persist_f64(cy2p_plan *plan, void *const *d_peer_buf0, void *const *d_peer_buf1,
+                                        int32_t world, int32_t rank, const uint32_t *d_row_peers, int32_t q_begin,
+                                        int32_t q_end, int32_t iters, void *const *d_peer_flags, int32_t *d_my_flags,
+                                        int32_t *d_epoch_counter, int32_t *d_error, void *stream) {
+    return rows_persist_impl<double>(plan, d_peer_buf0, d_peer_buf1, world, rank, d_row_peers, q_begin, q_end, iters,
+                                     d_peer_flags, d_my_flags, d_epoch_counter, d_error, stream);
 }
 
 int32_t cy2p_enable_peer_access(int32_t device, int32_t peer) {

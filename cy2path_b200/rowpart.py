@@ -269,6 +269,10 @@ class _Exchange:
             self.ptrs = [self.buf.data_ptr()]
             self.barrier = lambda: None
             self.kind = "none"
+            # the persistent single-start kernel runs its flag exchange even on one rank (against its own array)
+            self.flags = torch.zeros(64, dtype=torch.int32, device=dev)
+            self.flag_ptrs = torch.tensor([self.flags.data_ptr()], dtype=torch.int64, device=dev)
+            self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
             return
         import torch.distributed._symmetric_memory as symm
 
@@ -363,6 +367,20 @@ def propagate(rp, X0, iters, group=None, assemble=True, graph=None):
         barrier()  # every rank has mapped its peers and filled buffer 0
         use_graph = (B <= 8 and ex.kind in ("flags", "none")) if graph is None else bool(graph)
         done = 0
+        import os
+
+        if B == 1 and iters > 0 and ex.kind in ("flags", "none") and os.environ.get("CY2P_ROWPART_PERSIST", "0") != "0":
+            # opt-in experiment: ALL updates in one cooperative launch (grid barrier + in-kernel cross-GPU flag exchange
+            # per update, cy2p_propagate_rows_persist). Measured SLOWER than the graph of per-update launches: 120 vs 60 us
+            # per update at 10^6 cells on 2 GPUs (profiles/rowpart_check_2gpu_persist_r02.jsonl) — two grid barriers and a
+            # system-scope fence by every thread per update cost more than the two launches they replace
+            pfn = lib.cy2p_propagate_rows_persist_f64 if X0.dtype.itemsize == 8 else lib.cy2p_propagate_rows_persist
+            _lib.check(pfn(rp.plan.handle, ctypes.c_void_p(ex.ptr_arrays[0].data_ptr()),
+                           ctypes.c_void_p(ex.ptr_arrays[1].data_ptr()), world, rank, _lib.ptr(masks), rp.q0, rp.q1, iters,
+                           _lib.ptr(ex.flag_ptrs), _lib.ptr(ex.flags), _lib.ptr(ex.epoch), _lib.ptr(ex.error),
+                           _lib.stream_ptr(dev)))
+            done = iters
+            use_graph = False
         if use_graph and iters >= 8:
             key = (id(rp), B, X0.dtype)
             if getattr(ex, "graph_key", None) != key:

@@ -157,6 +157,21 @@ int32_t cy2p_propagate_rows_push_f64(cy2p_plan *plan, const double *d_Xp, void *
                                      void *stream);
 int32_t cy2p_enable_peer_access(int32_t device, int32_t peer);
 
+/* Row-partitioned single-start run (B == 1), ALL `iters` updates in ONE cooperative launch: per update the rank's rows
+ * [q_begin, q_end) are formed from its full-size iterate and pushed to the ranks that gather them (as
+ * cy2p_propagate_rows_push), followed by a grid barrier, the cross-GPU flag exchange of cy2p_xbarrier done by one CTA,
+ * and a second grid barrier — no launch and no host round trip per update. d_peer_buf0 / d_peer_buf1: device arrays of
+ * `world` pointers to every rank's two ping-pong iterates [n] (update 0 reads buffer 0 of this rank); flags / epoch
+ * counter / error word as for cy2p_xbarrier. All ranks must call it with the same `iters`. */
+int32_t cy2p_propagate_rows_persist(cy2p_plan *plan, void *const *d_peer_buf0, void *const *d_peer_buf1, int32_t world,
+                                    int32_t rank, const uint32_t *d_row_peers, int32_t q_begin, int32_t q_end,
+                                    int32_t iters, void *const *d_peer_flags, int32_t *d_my_flags,
+                                    int32_t *d_epoch_counter, int32_t *d_error, void *stream);
+int32_t cy2p_propagate_rows_persist_f64(cy2p_plan *plan, void *const *d_peer_buf0, void *const *d_peer_buf1,
+                                        int32_t world, int32_t rank, const uint32_t *d_row_peers, int32_t q_begin,
+                                        int32_t q_end, int32_t iters, void *const *d_peer_flags, int32_t *d_my_flags,
+                                        int32_t *d_epoch_counter, int32_t *d_error, void *stream);
+
 /* Cross-GPU barrier between two updates of the row-partitioned run, as ONE small kernel on `stream` (so it orders
  * after the rank's update kernel and can be captured in a CUDA graph): every rank writes its epoch into its slot of
  * every rank's flag array (d_peer_flags: device array of `world` pointers to the ranks' int32[world] flag arrays in

@@ -76,7 +76,7 @@ def test_float32_rows_and_public_driver_world1():
     from cy2path_b200 import _lib, rowpart
     from cy2path_b200.synth import batched_starts, knn_velocity_tpm
 
-    g = knn_velocity_tpm(6000, k=12, seed=43)
+    g = knn_velocity_tpm(6001, k=12, seed=43)  # a row count that is not a multiple of the rows a warp covers
     T = g["T"]
     X0 = batched_starts(T, 16, seed=2)
     ref = ofast.propagate_batch(T, X0, 12)
@@ -86,12 +86,22 @@ def test_float32_rows_and_public_driver_world1():
     for dt, tol in ((torch.float32, 1e-6), (torch.float64, 1e-13)):
         got = rowpart.propagate(rp, torch.from_numpy(X0).cuda().to(dt), 12)
         assert np.abs(got.cpu().numpy() - ref).max() <= tol
-    # B = 1 takes the CUDA-graph path (two updates per replay) for the even part and the eager path for the odd rest
+    # B = 1: the opt-in persistent kernel (all updates in one cooperative launch), then the default CUDA-graph path (two updates per
+    # replay) for the even part with the eager path for the odd rest
+    import os
+
     x1 = np.ascontiguousarray(X0[:, :1])
-    for iters in (13, 12, 3):
-        ref1 = ofast.propagate_batch(T, x1, iters)
-        got = rowpart.propagate(rp, torch.from_numpy(x1).cuda().double(), iters)
-        assert np.abs(got.cpu().numpy() - ref1).max() <= 1e-13
+    for persist in ("1", "0"):
+        os.environ["CY2P_ROWPART_PERSIST"] = persist
+        try:
+            for iters in (13, 12, 3, 1):
+                ref1 = ofast.propagate_batch(T, x1, iters)
+                got = rowpart.propagate(rp, torch.from_numpy(x1).cuda().double(), iters)
+                assert np.abs(got.cpu().numpy() - ref1).max() <= 1e-13
+                got32 = rowpart.propagate(rp, torch.from_numpy(x1).cuda(), iters)
+                assert np.abs(got32.cpu().numpy() - ref1).max() <= 1e-6
+        finally:
+            del os.environ["CY2P_ROWPART_PERSIST"]
 
 
 def test_config5_size_one_million_cells_against_scipy():

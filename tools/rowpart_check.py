@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=200_000)
     ap.add_argument("--iters", type=int, default=31)
+    ap.add_argument("--bench-n", type=int, default=0, help="also time B = 1 float64 at this size, persistent kernel on / off")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -59,6 +60,28 @@ def main():
                               "max_abs_vs_unsharded": float(errs[0]), "max_abs_vs_scipy_col0": float(errs[1]),
                               "rel_l1_vs_scipy_col0": float(errs[2]), "partition": rp.summary()["halo_rows_per_rank"],
                               "rows": rp.summary()["rows_per_rank"]}), flush=True)
+    if a.bench_n:
+        Tb, _ = shared_graph(a.bench_n, 5, rank, barrier)
+        rpb = rowpart.RowPartition(Tb, world, rank, device=local, sweeps=8)
+        x0 = torch.from_numpy(batched_starts(Tb, 1, seed=5)).cuda().double()
+        for persist in ("1", "0"):
+            os.environ["CY2P_ROWPART_PERSIST"] = persist
+            rowpart.propagate(rpb, x0, 10, assemble=False)
+            barrier()
+            res = []
+            for iters in (200, 0):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rowpart.propagate(rpb, x0, iters, assemble=False)
+                e1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                res.append(float(t))
+            if rank == 0:
+                print(json.dumps({"bench": "B=1 f64", "n": a.bench_n, "world": world, "persistent_kernel": persist == "1",
+                                  "us_per_update": (res[0] - res[1]) * 1e3 / 200}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
