@@ -86,7 +86,7 @@ struct cy2p_plan {
     double blk_reuse = 0.0;                // stored entries / distinct sources, averaged over the blocks
     // side stream + events of cy2p_fhmm_loss_grad (fhmm.cu): the node-level passes run beside the pass over D
     cudaStream_t side_stream = nullptr;
-    cudaEvent_t side_events[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t side_events[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace cy2p {

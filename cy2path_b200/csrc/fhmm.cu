@@ -2001,9 +2001,17 @@ FhmmWs fhmm_layout(int S, int L, int Le, int N, int I) {
     return w;
 }
 
+// Optional second stream for the dG contraction: dlogE (needed next, by the regulariser-gradient pass) and dG (needed only
+// by the backward recurrences) both read r and nothing else, so they run side by side.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;  // fork: recorded on the main stream after r is written; join: after dG
+};
+
 template <int KP>
 void launch_data_two_pass(int N, int I, int K, const FhmmWs &w, char *ws, const float *logE, const float *G,
-                          const float *D, float *pred, float *split, float *gG, double *div_acc, cudaStream_t st) {
+                          const float *D, float *pred, float *split, float *gG, double *div_acc, cudaStream_t st,
+                          SideStream side = SideStream()) {
     float *R = (float *)(ws + w.R);
     if (env_flag("CY2P_FHMM_MMA", 1)) {  // P, pred, divergence and r: the emission GEMM on the tensor cores
         constexpr int KT = (KP + 7) / 8;
@@ -2024,6 +2032,10 @@ void launch_data_two_pass(int N, int I, int K, const FhmmWs &w, char *ws, const 
     const int use_mma = env_flag("CY2P_FHMM_MMA", 1);
     if (use_mma) {  // the two gradients on the tensor cores (3xTF32), r read twice (mostly out of L2)
         const float inv_I = 1.0f / (float)I;
+        if (side.stream) {  // r is complete on the main stream: dG may start on the side stream
+            cudaEventRecord(side.fork, st);
+            cudaStreamWaitEvent(side.stream, side.fork, 0);
+        }
         {
             const int MT = (K + 15) / 16;
             const int tpad = (w.tchunk + 7) / 8 * 8;
@@ -2043,13 +2055,15 @@ void launch_data_two_pass(int N, int I, int K, const FhmmWs &w, char *ws, const 
             const size_t smem = sizeof(uint32_t) * 2 * (size_t)NT * 8 * kMmaLdE;
             dim3 grid((unsigned)((N + kMmaCells - 1) / kMmaCells));
             count_launch();
+            cudaStream_t sg = side.stream ? side.stream : st;
 #define DG_CASE(NT_)                                                                                                \
     case NT_:                                                                                                       \
         cudaFuncSetAttribute(fhmm_dG_mma<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-        fhmm_dG_mma<NT_><<<grid, 256, smem, st>>>(N, I, K, K, logE, R, gG, inv_I);                                  \
+        fhmm_dG_mma<NT_><<<grid, 256, smem, sg>>>(N, I, K, K, logE, R, gG, inv_I);                                  \
         break;
             switch (NT) { DG_CASE(1) DG_CASE(2) DG_CASE(3) DG_CASE(4) DG_CASE(5) DG_CASE(6) DG_CASE(7) DG_CASE(8) }
 #undef DG_CASE
+            if (side.stream) cudaEventRecord(side.join, side.stream);
         }
         return;
     }
@@ -2073,14 +2087,15 @@ void launch_data_pass(int N, int I, int K, const FhmmWs &w, const float *logE, c
 }
 
 void dispatch_data_pass(int N, int I, int K, const FhmmWs &w, char *ws, const float *logE, const float *G,
-                        const float *D, float *pred, float *split, float *gG, double *div_acc, cudaStream_t st) {
+                        const float *D, float *pred, float *split, float *gG, double *div_acc, cudaStream_t st,
+                        SideStream side = SideStream()) {
 #define CASE(KP_, J_)                                                                         \
     case KP_:                                                                                 \
         launch_data_pass<KP_, J_>(N, I, K, w, logE, G, D, pred, split, gG, div_acc, st);      \
         break;
 #define CASE2(KP_)                                                                                \
     case KP_:                                                                                     \
-        launch_data_two_pass<KP_>(N, I, K, w, ws, logE, G, D, pred, split, gG, div_acc, st);      \
+        launch_data_two_pass<KP_>(N, I, K, w, ws, logE, G, D, pred, split, gG, div_acc, st, side); \
         break;
     if (w.two_pass) {
         switch (w.KP) {
@@ -2425,7 +2440,7 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
     if (env_flag("CY2P_FHMM_OVERLAP", 1)) {
         if (!plan->side_stream) {
             CY2P_CUDA(cudaStreamCreateWithFlags(&plan->side_stream, cudaStreamNonBlocking));
-            for (int i = 0; i < 4; ++i) CY2P_CUDA(cudaEventCreateWithFlags(&plan->side_events[i], cudaEventDisableTiming));
+            for (int i = 0; i < 6; ++i) CY2P_CUDA(cudaEventCreateWithFlags(&plan->side_events[i], cudaEventDisableTiming));
         }
         s2 = plan->side_stream;
         CY2P_CUDA(cudaEventRecord(ev[0], st));  // fork: the memsets and the caller's earlier work
@@ -2442,9 +2457,10 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
         CY2P_CUDA(cudaStreamWaitEvent(st, ev[2], 0));
         CY2P_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
     }
-    // pass over D (main stream)
-    dispatch_data_pass(N, I, K, w, ws, logE, (const float *)(ws + w.G), d_D, nullptr, (float *)(ws + w.split),
-                       (float *)(ws + w.gG), scal + sc.div, st);
+    // pass over D (main stream; with two streams and the tensor-core path, dG runs on the side stream after the
+    // node-level arm that is queued there below, and is joined before the backward recurrences)
+    SideStream dg_side;
+    const bool dg_on_side = two && w.two_pass && env_flag("CY2P_FHMM_MMA", 1);
     // node-level conditionals and their products with T (side stream)
     const unsigned gN = (unsigned)((N + 127) / 128);
     count_launch();
@@ -2465,10 +2481,15 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
     lse_partials<<<nparts, 256, 0, s2>>>(N, (const double *)(ws + w.llv), (double2 *)(ws + w.llpart));
     count_launch();
     lse_combine<<<1, 256, 0, s2>>>(nparts, (const double2 *)(ws + w.llpart), scal + sc.ll);
-    if (two) {
-        CY2P_CUDA(cudaEventRecord(ev[3], s2));  // join
-        CY2P_CUDA(cudaStreamWaitEvent(st, ev[3], 0));
+    if (two) CY2P_CUDA(cudaEventRecord(ev[3], s2));  // the node-level arm is complete
+    if (dg_on_side) {
+        dg_side.stream = s2;
+        dg_side.fork = ev[4];
+        dg_side.join = ev[5];
     }
+    dispatch_data_pass(N, I, K, w, ws, logE, (const float *)(ws + w.G), d_D, nullptr, (float *)(ws + w.split),
+                       (float *)(ws + w.gG), scal + sc.div, st, dg_side);
+    if (two) CY2P_CUDA(cudaStreamWaitEvent(st, ev[3], 0));
     count_launch();
     fhmm_node_pass_c<<<gN, 128, 0, st>>>(S, L, Le, N, K, w.nsplit, logE, (const float *)(ws + w.aux), X1, X2, Y1, TP,
                                          (const float *)(ws + w.split), scal, w_excl, w_orth, w_tpm, d_gE);
@@ -2476,6 +2497,7 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
     fhmm_emission_grad_finish<<<(unsigned)(((int64_t)K * N + 255) / 256), 256, 0, st>>>(N, K, logE, scal + sc.rowsum,
                                                                                        d_gE);
     // small backward
+    if (dg_on_side) CY2P_CUDA(cudaStreamWaitEvent(st, ev[5], 0));  // dG (side stream) is complete
     const int NB = (I + w.P - 1) / w.P;
     CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_local));
     count_launch();
