@@ -175,7 +175,11 @@ __device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int
     double uv[CPL], uu[CPL];
 #pragma unroll
     for (int k = 0; k < CPL; ++k) uv[k] = uu[k] = 0.0;
-    if (EPS) {
+    // EPS is compiled in for every launch (the instantiation WITHOUT the partial sums gets a worse schedule from ptxas:
+    // 3.69 vs 2.70 ms per update, profiles/k1x_sweep5_noeps_r02.jsonl); a call without a stationary vector passes
+    // eps_acc == null and only skips the epilogue
+    const bool want_eps = EPS && a.eps_acc != nullptr;
+    if (want_eps) {
         for (int t = threadIdx.x; t < 2 * CPL * 32; t += WARPS * 32) (&s_acc[0][0][0])[t] = 0ull;
         if (threadIdx.x == 0) *s_done = 0u;
         __syncthreads();
@@ -206,7 +210,7 @@ __device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int
             const int32_t rn = r + WARPS;
             int32_t pn = 0, endn = 0;
             if (rn < row1) pn = __ldg(a.indptr + rn), endn = __ldg(a.indptr + rn + 1);
-            const double pi = EPS ? __ldg(a.pi_rows + r) : 0.0;
+            const double pi = want_eps ? __ldg(a.pi_rows + r) : 0.0;
             const int32_t orow = (OUT_F32 && a.out_orig) ? __ldg(a.dest_ids + r) : r;
             double acc[CPL];
 #pragma unroll
@@ -313,7 +317,7 @@ __device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int
             }
         }
     }
-    if (EPS) {
+    if (want_eps) {
         const double sc = __ldg(a.eps_scale);
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
@@ -395,7 +399,7 @@ spmm_gather_x_multi(int32_t n_rows, int32_t rows_per_item, int32_t nslabs, int32
         XArgs b = a;
         b.xin = src_is_A ? bufA : bufB;
         b.xout = src_is_A ? bufB : bufA;
-        if (EPS) b.eps_acc = a.eps_acc + (size_t)it * eps_stride;
+        if (EPS && a.eps_acc) b.eps_acc = a.eps_acc + (size_t)it * eps_stride;
         for (;;) {
             if (threadIdx.x == 0) s_item = atomicAdd(counters + it, 1);
             __syncthreads();
@@ -594,19 +598,13 @@ static void x_launch_t(const XArgs &a, int32_t n, int rows_per_cta, cudaStream_t
         if (ps.counter) {
             count_launch();
             const int ctas = ps.num_sms * MINB;
-            if (a.eps_acc)
-                spmm_gather_x_persist<LOB, CPL, WARPS, MINB, U, true><<<ctas, WARPS * 32, 0, st>>>(n, rows_per_cta, nslabs, ps.counter, a);
-            else
-                spmm_gather_x_persist<LOB, CPL, WARPS, MINB, U, false><<<ctas, WARPS * 32, 0, st>>>(n, rows_per_cta, nslabs, ps.counter, a);
+            spmm_gather_x_persist<LOB, CPL, WARPS, MINB, U, true><<<ctas, WARPS * 32, 0, st>>>(n, rows_per_cta, nslabs, ps.counter, a);
             return;
         }
     }
     const dim3 grid((unsigned)((n + rows_per_cta - 1) / rows_per_cta), (unsigned)nslabs);
     count_launch();
-    if (a.eps_acc)
-        spmm_gather_x<LOB, CPL, WARPS, MINB, U, IN_F32, OUT_F32, true><<<grid, WARPS * 32, 0, st>>>(0, n, rows_per_cta, a);
-    else
-        spmm_gather_x<LOB, CPL, WARPS, MINB, U, IN_F32, OUT_F32, false><<<grid, WARPS * 32, 0, st>>>(0, n, rows_per_cta, a);
+    spmm_gather_x<LOB, CPL, WARPS, MINB, U, IN_F32, OUT_F32, true><<<grid, WARPS * 32, 0, st>>>(0, n, rows_per_cta, a);
 }
 
 // tile -> tile updates (the bulk of a run): the tuning knobs select the instantiation. Measured on B200 at config 2
@@ -765,11 +763,9 @@ int32_t cy2p_propagate_x(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t 
                 count_launch();
                 cudaError_t le;
                 if (c.lob == 16)
-                    le = d_eps ? cudaLaunchCooperativeKernel((void *)spmm_gather_x_multi<16, 4, 8, 2, 4, true>, grid, dim3(256), args, 0, st)
-                               : cudaLaunchCooperativeKernel((void *)spmm_gather_x_multi<16, 4, 8, 2, 4, false>, grid, dim3(256), args, 0, st);
+                    le = cudaLaunchCooperativeKernel((void *)spmm_gather_x_multi<16, 4, 8, 2, 4, true>, grid, dim3(256), args, 0, st);
                 else
-                    le = d_eps ? cudaLaunchCooperativeKernel((void *)spmm_gather_x_multi<8, 4, 8, 2, 4, true>, grid, dim3(256), args, 0, st)
-                               : cudaLaunchCooperativeKernel((void *)spmm_gather_x_multi<8, 4, 8, 2, 4, false>, grid, dim3(256), args, 0, st);
+                    le = cudaLaunchCooperativeKernel((void *)spmm_gather_x_multi<8, 4, 8, 2, 4, true>, grid, dim3(256), args, 0, st);
                 CY2P_CUDA(le);
                 if (n_upd & 1) src = dst;  // an odd number of updates ends in the other buffer
                 it += n_upd - 1;

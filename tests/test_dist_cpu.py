@@ -162,3 +162,64 @@ def test_row_peer_masks_are_sufficient_for_a_halo_exchange():
         if world >= 2:
             pushed = sum(int(((masks >> np.uint32(p)) & np.uint32(1)).sum()) for p in range(world)) - n
             assert pushed < 0.7 * (world - 1) * n  # the halo is well below the all-gather's (world-1)*n rows
+
+
+def _rowpart_worker(rank, world, port, out_dir):
+    """Two processes, each with its OWN RowPartition (order, refined blocks, masks, matrix slice built independently
+    from the same T): per update a rank forms its rows from its slice of T and a full-size iterate in which only own
+    rows + halo were ever written (the rest is NaN), and sends each peer exactly the rows whose mask names that peer."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cy2path_b200 import rowpart
+        from cy2path_b200.synth import batched_starts, knn_velocity_tpm
+        from oracle import fast as ofast
+
+        g = knn_velocity_tpm(2500, k=10, seed=19)
+        T = g["T"]
+        n = T.shape[0]
+        rp = rowpart.RowPartition(T, world, rank, build_plan=False)
+        TtP = rowpart.permuted_transpose(T, rp.order)
+        mine = rowpart.sliced_matrix(TtP, rp.q0, rp.q1)  # the rank's share of T: only destinations in [q0, q1)
+        assert mine.nnz == rp.nnz_local < T.nnz
+        X0 = batched_starts(T, 3, seed=2).astype(np.float64)
+        peer = 1 - rank
+        bit_me, bit_peer = np.uint32(1 << rank), np.uint32(1 << peer)
+        buf = np.full((n, 3), np.nan)
+        need = (rp.masks & bit_me) != 0
+        buf[need] = X0[rp.order][need]
+        send_rows = np.nonzero((rp.masks[rp.q0:rp.q1] & bit_peer) != 0)[0] + rp.q0
+        cnt = torch.tensor([len(send_rows)])
+        cnts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        for _ in range(8):
+            rows = (mine.T.tocsr()[rp.q0:rp.q1].astype(np.float64) @ np.nan_to_num(buf, nan=np.inf))
+            nxt = np.full((n, 3), np.nan)
+            nxt[rp.q0:rp.q1] = rows
+            out_t = torch.from_numpy(np.ascontiguousarray(rows[send_rows - rp.q0]))
+            idx_t = torch.from_numpy(send_rows.astype(np.int64))
+            in_t = torch.empty((int(cnts[peer]), 3), dtype=torch.float64)
+            in_idx = torch.empty(int(cnts[peer]), dtype=torch.int64)
+            ops = [dist.isend(out_t, peer), dist.isend(idx_t, peer)] if rank == 0 else []
+            dist.recv(in_t, peer)
+            dist.recv(in_idx, peer)
+            if rank == 1:
+                ops = [dist.isend(out_t, peer), dist.isend(idx_t, peer)]
+            for o in ops:
+                o.wait()
+            nxt[in_idx.numpy()] = in_t.numpy()
+            buf = nxt
+        assert np.isfinite(buf[rp.q0:rp.q1]).all()
+        ref = ofast.propagate_batch(T, X0, 8)[rp.order]
+        assert np.abs(buf[rp.q0:rp.q1] - ref[rp.q0:rp.q1]).max() <= 1e-15
+        assert np.isnan(buf).any()  # rows this rank never gathers were never sent to it
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_rowpart_halo_exchange_world2_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_rowpart_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
