@@ -17,6 +17,7 @@ that holds the north_star's 1e-6 relative-L1 bar at 2,000 iterations (tests/test
 iterate's rate is reported under detail.fp32_outside_tolerance, labelled as such.
 
 Besides the headline (config 2) the same run reports, under "detail" (skipped with --no-extras):
+  config1_single_start  3,696 cells, 1 start, 1,000 updates with the full float64 history (the reference's own case)
   config3_fhmm     factorial latent model, S=10 L=4 N=50,000 I=500: ms per epoch (loss + analytic gradients + RMSprop)
   config4_strong   250,000-cell TPM, 4,096 starts split 4,096/N per GPU, a 100-iteration slice of the 1,000
   config5_rowpart  1,000,000-cell TPM row-partitioned over the N GPUs, B = 1 and B = 256, fused update + halo push
@@ -447,6 +448,85 @@ def extra_config5(rank, world, dev, barrier):
     return out
 
 
+def extra_config1(rank, dev):
+    """BASELINE config 1 (the reference's own CPU-runnable case): 3,696-cell TPM, ONE start distribution (the root-cell
+    prior), 1,000 updates with the full float64 history and eps — `iterate_state_probability` as the reference calls it.
+    Device-resident time of the propagation, end-to-end time through the public function (plan build, H2D, D2H of the
+    29.6 MB history), and the reference's own function on one host core (scipy's product is single-threaded)."""
+    import torch
+
+    import cy2path_b200 as c2p
+    from cy2path_b200 import _lib
+    from cy2path_b200.sampling import clear_plan_cache, get_plan
+    from cy2path_b200.synth import knn_velocity_tpm
+
+    if rank != 0:
+        return None
+    n, iters = 3696, 1000
+    g = knn_velocity_tpm(n, k=30, seed=1)
+    T = g["T"]
+    init = g["root_cells"] / g["root_cells"].sum()
+    stat = g["end_points"] / g["end_points"].sum()
+    plan = get_plan(T)
+    x0 = torch.from_numpy(init).to(dev)
+    st = torch.from_numpy(stat).to(dev)
+    for _ in range(3):
+        _lib.propagate(plan, x0, iters, stationary=st, want_final=False, history_stride=1, want_eps=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        _lib.propagate(plan, x0, iters, stationary=st, want_final=False, history_stride=1, want_eps=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+
+    class A:
+        pass
+
+    ad = A()
+    ad.obsp, ad.shape, ad.uns = {"T_forward": T}, (n, 0), {}
+    c2p.iterate_state_probability(ad, init=init, stationary=stat, max_iter=iters)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        clear_plan_cache()
+        _, hist, conv = c2p.iterate_state_probability(ad, init=init, stationary=stat, max_iter=iters)
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    out = {"workload": "3,696 cells, 1 start (root prior), 1,000 updates, full float64 history + eps",
+           "ms_device": ms, "us_per_update": ms * 1e3 / iters, "cell_iterations_per_s": n * iters / (ms * 1e-3),
+           "ms_e2e_public_api": e2e_ms, "e2e_cell_iterations_per_s": n * iters / (e2e_ms * 1e-3), "convergence": int(conv)}
+    try:  # the reference's own function (oracle/_ref) or the oracle port, one core: the cpu_baseline leg
+        if reference_available():
+            import logging
+
+            os.environ["TQDM_DISABLE"] = "1"
+            from oracle import ref_shim
+
+            ref = ref_shim.load()
+            logging.disable(logging.WARNING)
+            adr = ref_shim.DuckAnnData(T)
+            t0 = time.perf_counter()
+            _, rh, rconv = ref.sampling.iterate_state_probability(adr, init=init, stationary=stat, max_iter=iters)
+            cpu_s = time.perf_counter() - t0
+            logging.disable(logging.NOTSET)
+            kind = "reference"
+            out["max_abs_vs_reference_history"] = float(np.abs(hist - rh).max())
+            out["same_convergence_as_reference"] = bool(int(rconv) == int(conv))
+        else:
+            from oracle import msm as omsm
+
+            t0 = time.perf_counter()
+            omsm.iterate_state_probability(T, init, stat, max_iter=iters)
+            cpu_s = time.perf_counter() - t0
+            kind = "port"
+        out["cpu_baseline"] = {"ms": cpu_s * 1e3, "cell_iterations_per_s": n * iters / cpu_s, "cores": 1, "kind": kind,
+                               "sample": "the whole config (1,000 updates), one call"}
+    except Exception as e:  # pragma: no cover
+        out["cpu_baseline"] = {"error": repr(e)[:200]}
+    return out
+
+
 def ncu_reference(kernel_prefix, grid):
     """dram bytes and L2 -> L1 sectors per launch of the dominant kernel from the committed ncu summary of this
     round's capture (profiles/ncu_k1_current_summary.json, written by tools/ncu_summary.py); None when the capture is
@@ -685,7 +765,8 @@ def run_b200(args, w):
 
     extras = {}
     if not args.no_extras and args.workload == "config2" and os.environ.get("CY2P_BENCH_EXTRAS", "1") != "0":
-        for name, fn in (("config3_fhmm", lambda: extra_config3(rank, dev, T, plan)),
+        for name, fn in (("config1_single_start", lambda: extra_config1(rank, dev)),
+                         ("config3_fhmm", lambda: extra_config3(rank, dev, T, plan)),
                          ("config4_strong", lambda: extra_config4(rank, world, dev, barrier, peak)),
                          ("config5_rowpart", lambda: extra_config5(rank, world, dev, barrier))):
             t_ex = time.perf_counter()
