@@ -382,12 +382,16 @@ def propagate(rp, X0, iters, group=None, assemble=True, graph=None):
             done = iters
             use_graph = False
         if use_graph and iters >= 8:
-            key = (id(rp), B, X0.dtype)
-            if getattr(ex, "graph_key", None) != key:
+            # the captured graph holds raw pointers into THIS partition's plan and THIS exchange's buffers: it lives on
+            # the partition object, next to a reference to the exchange, so neither can be freed (or their addresses
+            # reused by another object) while the graph exists
+            graphs = rp.__dict__.setdefault("_graphs", {})
+            key = (B, X0.dtype)
+            hit = graphs.get(key)
+            if hit is None or hit[1] is not ex:
                 update(0)  # warm up outside the capture (lazy module loading); two updates: back to buffer 0
                 update(1)
                 torch.cuda.synchronize(dev)
-                buf[0].copy_(X0.index_select(0, order))
                 side = torch.cuda.Stream(device=dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
                 g = torch.cuda.CUDAGraph()
@@ -396,13 +400,13 @@ def propagate(rp, X0, iters, group=None, assemble=True, graph=None):
                         update(0)
                         update(1)
                 torch.cuda.current_stream(dev).wait_stream(side)
-                ex.graph, ex.graph_key = g, key
+                graphs[key] = hit = (g, ex)
                 buf[0].copy_(X0.index_select(0, order))
                 if world > 1:
                     dist.barrier(group=group)
                 barrier()
             for _ in range(iters // 2):
-                ex.graph.replay()
+                hit[0].replay()
             done = iters // 2 * 2
         for it in range(done, iters):
             update(it & 1)
