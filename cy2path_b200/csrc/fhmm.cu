@@ -667,6 +667,26 @@ fhmm_fwd_mma(int N, int I, int K, int ldG, int tchunk, const float *__restrict__
     }
     __syncthreads();
     double div = 0.0;
+    const bool vec = (N & 1) == 0;
+    auto load_d = [&](int tb_, float2 (&dst)[NW][2]) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = t0 + tb_ + g + 8 * h, n = nbase + 8 * w + 2 * tg;
+                dst[w][h] = make_float2(0.f, 0.f);
+                if (D != nullptr && tb_ < tpad && t < t1) {
+                    const float *dp = D + (size_t)t * N + n;
+                    if (vec && n + 1 < N) dst[w][h] = __ldg(reinterpret_cast<const float2 *>(dp));
+                    else {
+                        if (n < N) dst[w][h].x = __ldg(dp);
+                        if (n + 1 < N) dst[w][h].y = __ldg(dp + 1);
+                    }
+                }
+            }
+    };
+    float2 dnext[NW][2];
+    load_d(0, dnext);
     for (int tb = 0; tb < tpad; tb += 16) {
         uint32_t ah[KT][4], al[KT][4];
 #pragma unroll
@@ -676,25 +696,15 @@ fhmm_fwd_mma(int N, int I, int K, int ldG, int tchunk, const float *__restrict__
             al[q][0] = pl[0], al[q][1] = pl[8 * LD], al[q][2] = pl[4], al[q][3] = pl[8 * LD + 4];
         }
         float div_f = 0.f;
-        // the D values of this block of time steps are requested before the MMAs so that the two overlap: lane (g, tg)
-        // owns rows t = g, g + 8 and the column pair (2tg, 2tg + 1) of every tile (one 8-byte access when N is even)
+        // the D values are requested ONE BLOCK of 16 time steps AHEAD (and those of the first block before the loop), so
+        // that their HBM latency hides behind a whole block of MMAs and elementwise work: lane (g, tg) owns rows
+        // t = g, g + 8 and the column pair (2tg, 2tg + 1) of every tile (one 8-byte access when N is even)
         float2 dv[NW][2];
-        const bool vec = (N & 1) == 0;
 #pragma unroll
         for (int w = 0; w < NW; ++w)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int t = t0 + tb + g + 8 * h, n = nbase + 8 * w + 2 * tg;
-                dv[w][h] = make_float2(0.f, 0.f);
-                if (D != nullptr && t < t1) {
-                    const float *dp = D + (size_t)t * N + n;
-                    if (vec && n + 1 < N) dv[w][h] = __ldg(reinterpret_cast<const float2 *>(dp));
-                    else {
-                        if (n < N) dv[w][h].x = __ldg(dp);
-                        if (n + 1 < N) dv[w][h].y = __ldg(dp + 1);
-                    }
-                }
-            }
+            for (int h = 0; h < 2; ++h) dv[w][h] = dnext[w][h];
+        load_d(tb + 16, dnext);
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -818,7 +828,7 @@ fhmm_dE_mma(int N, int I, int K, int Kfull, int ldG, int tchunk, const float *__
 // takes blocks of 16 time steps, A = r in the row-major fragment layout (each lane reads 4 floats of 4 different
 // rows; a warp covers 16 rows x 32 bytes = whole sectors), B = E^T from shared memory, NT = ceil(K / 8) accumulator
 // tiles; one atomic per (t, k) and CTA at the end of a block of time steps.
-constexpr int kMmaCells = 64, kMmaLdE = kMmaCells + 4;
+constexpr int kMmaCells = 128, kMmaLdE = kMmaCells + 4;
 template <int NT>
 __global__ void __launch_bounds__(256)
 fhmm_dG_mma(int N, int I, int K, int Kfull, const float *__restrict__ logE, const float *__restrict__ R,
