@@ -59,7 +59,7 @@ def gather_ragged_int64(values, group=None):
     return np.concatenate([o[: int(c.item())].cpu().numpy() for o, c in zip(outs, counts)])
 
 
-def propagate_batch_sharded(T, X0, iters, stationary=None, tol=1e-5, group=None, precision="fp32", gather=True):
+def propagate_batch_sharded(T, X0, iters, stationary=None, tol=1e-5, group=None, precision="f48", gather=True):
     """Batch-sharded MSM simulation: this rank propagates its own columns X0 [n, B_local].
 
     Returns the local result dict of ``sampling.propagate_batch`` plus, when ``gather`` and a
