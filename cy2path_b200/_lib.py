@@ -18,7 +18,8 @@ OK, ERR_INVALID_ARG, ERR_BAD_CSR, ERR_CDF_OVERSHOOT, ERR_CUDA, ERR_WORKSPACE, ER
 
 # every symbol the header declares (tests check the built library exports all of them)
 SYMBOLS = [
-    "cy2p_abi_version", "cy2p_last_error", "cy2p_launch_count", "cy2p_plan_create", "cy2p_plan_create_host", "cy2p_plan_destroy",
+    "cy2p_abi_version", "cy2p_last_error", "cy2p_launch_count", "cy2p_plan_create", "cy2p_plan_create_host",
+    "cy2p_plan_create_host_f64", "cy2p_plan_destroy",
     "cy2p_plan_info", "cy2p_propagate_ws_bytes", "cy2p_propagate_column_tile", "cy2p_propagate", "cy2p_propagate_rows",
     "cy2p_propagate_f64_ws_bytes", "cy2p_propagate_f64", "cy2p_propagate_rows_f64", "cy2p_plan_order",
     "cy2p_propagate_x_ws_bytes", "cy2p_propagate_x_column_tile", "cy2p_propagate_x", "cy2p_order_host", "cy2p_xbarrier", "cy2p_propagate_rows_persist", "cy2p_propagate_rows_persist_f64",
@@ -54,6 +55,7 @@ def load():
     lib.cy2p_launch_count.restype = _i64
     lib.cy2p_plan_create.argtypes = [_i32, _i64, _vp, _vp, _vp, _i32, _vp, ctypes.POINTER(_vp)]
     lib.cy2p_plan_create_host.argtypes = lib.cy2p_plan_create.argtypes
+    lib.cy2p_plan_create_host_f64.argtypes = lib.cy2p_plan_create.argtypes
     lib.cy2p_plan_destroy.argtypes = [_vp]
     lib.cy2p_plan_info.argtypes = [_vp, ctypes.POINTER(_i64)]
     lib.cy2p_propagate_ws_bytes.argtypes = [_vp, _i32, _i32]
@@ -213,21 +215,26 @@ class Plan:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         indptr = np.ascontiguousarray(T.indptr, dtype=np.int32)
         indices = np.ascontiguousarray(T.indices, dtype=np.int32)
-        if np.asarray(T.data).dtype == np.float64:
-            import warnings
-
-            data32 = np.asarray(T.data, dtype=np.float32)
-            if not np.array_equal(data32.astype(np.float64), T.data):
-                warnings.warn("the transition matrix holds float64 values that are not exactly representable in float32; "
-                              "the device plan stores float32 (scvelo's dtype): results follow the ROUNDED matrix, which "
-                              "leaves the reference's float64 product by ~2e-9 relative L1 per iteration "
-                              "(INTEGRATION.md §1). Pass T.astype(np.float32) to silence this.", stacklevel=3)
-        data = np.ascontiguousarray(T.data, dtype=np.float32)
+        # A float64 matrix whose values are not float32-representable is held as hi + lo float32 pairs (48 mantissa
+        # bits): the float64-arithmetic paths (single-start float64, batched f48 / f40) and the CDF tables then follow
+        # the reference's float64 product / cumsum (sampling.py:40-42, simulation.py:24-25). The float32 / legacy fp64
+        # batched kernels, the row-partitioned run and the FHMM operand use hi alone.
+        self.float64_matrix = False
         handle = _vp(0)
-        with torch.cuda.device(self.device):
-            check(lib.cy2p_plan_create_host(self.n, self.nnz, indptr.ctypes.data, indices.ctypes.data,
-                                            data.ctypes.data, self.device.index, stream_ptr(self.device),
-                                            ctypes.byref(handle)))
+        if np.asarray(T.data).dtype == np.float64:
+            data64 = np.ascontiguousarray(T.data, dtype=np.float64)
+            self.float64_matrix = not np.array_equal(data64.astype(np.float32).astype(np.float64), data64)
+        if self.float64_matrix:
+            with torch.cuda.device(self.device):
+                check(lib.cy2p_plan_create_host_f64(self.n, self.nnz, indptr.ctypes.data, indices.ctypes.data,
+                                                    data64.ctypes.data, self.device.index, stream_ptr(self.device),
+                                                    ctypes.byref(handle)))
+        else:
+            data = np.ascontiguousarray(T.data, dtype=np.float32)
+            with torch.cuda.device(self.device):
+                check(lib.cy2p_plan_create_host(self.n, self.nnz, indptr.ctypes.data, indices.ctypes.data,
+                                                data.ctypes.data, self.device.index, stream_ptr(self.device),
+                                                ctypes.byref(handle)))
         self.handle = handle
         info = (_i64 * 8)()
         check(lib.cy2p_plan_info(self.handle, info))

@@ -75,6 +75,13 @@ struct cy2p_plan {
     double span_identity = 0.0, span_reordered = 0.0;  // mean |pos(i) - pos(j)| over the stored entries
     // float64-valued copies of the three pair arrays (built on first use by propagate_x.cu)
     cy2p::PairD *d_t_pairsD = nullptr, *d_r_pairsD_pp = nullptr, *d_r_pairsD_op = nullptr;
+    // A float64 transition matrix (cy2p_plan_create_host_f64) is held as value = hi + lo with hi = float32(value) in
+    // the arrays above and lo = float32(value - hi) here, entry for entry: (double)hi + (double)lo restores 48 mantissa
+    // bits, which is what the float64-arithmetic paths (single-start float64, batched f48) multiply by. Null for a
+    // float32 matrix.
+    float *d_data_lo = nullptr;  // CSR order (with d_data)
+    float *d_t_lo = nullptr;     // T^T order (with d_t_pairs)
+    float *d_r_lo_pp = nullptr, *d_r_lo_op = nullptr;  // with d_r_pairs_pp / d_r_pairs_op
     // Staged gather (propagate.cu spmm_staged): the permuted rows cut into blocks whose distinct sources fit a CTA's
     // shared memory; sources are named by their index in the block's list
     int32_t nblk = 0;                      // 0 = not built

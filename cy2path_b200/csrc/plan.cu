@@ -81,6 +81,12 @@ __global__ void fill_pairs_kernel(int64_t nnz, const int32_t *__restrict__ sorte
     pairs[q] = e;
 }
 
+__global__ void fill_lo_kernel(int64_t nnz, const int32_t *__restrict__ sorted_ordinal, const float *__restrict__ lo_csr,
+                               float *__restrict__ t_lo) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nnz) t_lo[q] = lo_csr[sorted_ordinal[q]];
+}
+
 // CDF width W = max over rows of the number of non-zeros of the DENSE row (reference
 // simulation.py:28-41 uses count_nonzero(T.toarray())): distinct columns whose summed value != 0.
 __global__ void cdf_width_kernel(int32_t n, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
@@ -113,9 +119,12 @@ __global__ void cdf_width_kernel(int32_t n, const int32_t *__restrict__ indptr, 
 
 // extract_nonzero_entries, one thread per row. fp32 sequential adds in storage order; the rounding is
 // numpy's round(x, 3) on float32: rint(x * 1000f) / 1000f, each op rounded to fp32 (no FMA contraction).
+// lo != null (float64 matrix): the reference's cumsum runs in the matrix's dtype (simulation.py:24-25), is cast to
+// float32 on assignment (:44-46) and rounded there (:49-51) — sequential float64 adds of hi + lo, one cast, same rounding.
 __global__ void cdf_build_kernel(int32_t n, int32_t W, const int32_t *__restrict__ indptr,
                                  const int32_t *__restrict__ indices, const float *__restrict__ data,
-                                 int32_t *__restrict__ idx, float *__restrict__ cum, int32_t *flag_too_long) {
+                                 const float *__restrict__ lo, int32_t *__restrict__ idx, float *__restrict__ cum,
+                                 int32_t *flag_too_long) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int32_t s = indptr[i], e = indptr[i + 1];
@@ -124,9 +133,15 @@ __global__ void cdf_build_kernel(int32_t n, int32_t W, const int32_t *__restrict
         e = s + W;
     }
     float run = 0.f;
+    double run64 = 0.0;
     int32_t j = 0;
     for (int32_t p = s; p < e; ++p, ++j) {
-        run = __fadd_rn(run, data[p]);
+        if (lo != nullptr) {
+            run64 = __dadd_rn(run64, __dadd_rn((double)data[p], (double)lo[p]));
+            run = __double2float_rn(run64);
+        } else {
+            run = __fadd_rn(run, data[p]);
+        }
         idx[(size_t)i * W + j] = indices[p];
         cum[(size_t)i * W + j] = __fdiv_rn(rintf(__fmul_rn(run, 1000.f)), 1000.f);
     }
@@ -175,6 +190,10 @@ static void plan_free(cy2p_plan *p) {
     if (p->side_stream) cudaStreamDestroy(p->side_stream);
     for (cudaEvent_t e : p->side_events)
         if (e) cudaEventDestroy(e);
+    cudaFree(p->d_data_lo);
+    cudaFree(p->d_t_lo);
+    cudaFree(p->d_r_lo_pp);
+    cudaFree(p->d_r_lo_op);
     cudaFree(p->d_t_pairsD);
     cudaFree(p->d_r_pairsD_pp);
     cudaFree(p->d_r_pairsD_op);
@@ -182,7 +201,8 @@ static void plan_free(cy2p_plan *p) {
 }
 
 static int32_t plan_build(int32_t n, int64_t nnz, const int32_t *indptr, const int32_t *indices, const float *data,
-                          cudaMemcpyKind kind, int32_t device, cudaStream_t st, cy2p_plan **out) {
+                          cudaMemcpyKind kind, int32_t device, cudaStream_t st, cy2p_plan **out,
+                          const float *lo = nullptr /* residuals of a float64 matrix, same order and memory space as data */) {
     CY2P_REQUIRE(out != nullptr, "out is null");
     *out = nullptr;
     CY2P_REQUIRE(n > 0 && nnz >= 0 && nnz < (int64_t)INT32_MAX, "n must be > 0 and 0 <= nnz < 2^31");
@@ -226,6 +246,11 @@ static int32_t plan_build(int32_t n, int64_t nnz, const int32_t *indptr, const i
     if (nnz) {
         TRY_CUDA(cudaMemcpyAsync(plan->d_indices, indices, sizeof(int32_t) * (size_t)nnz, kind, st));
         TRY_CUDA(cudaMemcpyAsync(plan->d_data, data, sizeof(float) * (size_t)nnz, kind, st));
+        if (lo != nullptr) {
+            TRY(dmalloc(plan, &plan->d_data_lo, (size_t)nnz, st));
+            TRY(dmalloc(plan, &plan->d_t_lo, (size_t)nnz, st));
+            TRY_CUDA(cudaMemcpyAsync(plan->d_data_lo, lo, sizeof(float) * (size_t)nnz, kind, st));
+        }
     }
 
     // temporaries (freed before return)
@@ -308,6 +333,10 @@ static int32_t plan_build(int32_t n, int64_t nnz, const int32_t *indptr, const i
         TRY_CUDA_T(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp_sort, plan->d_indices, key_out, ord_in, ord_out,
                                                    (int)nnz, 0, end_bit, st));
         count_launch(); fill_pairs_kernel<<<gz, TB, 0, st>>>(nnz, ord_out, rowid, plan->d_data, plan->d_t_pairs);
+        if (plan->d_data_lo) {
+            count_launch();
+            fill_lo_kernel<<<gz, TB, 0, st>>>(nnz, ord_out, plan->d_data_lo, plan->d_t_lo);
+        }
     }
     TRY_CUDA_T(cudaGetLastError());
     TRY_CUDA_T(cudaMemcpyAsync(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
@@ -346,6 +375,21 @@ int32_t cy2p_plan_create_host(int32_t n, int64_t nnz, const int32_t *h_indptr, c
                       out);
 }
 
+int32_t cy2p_plan_create_host_f64(int32_t n, int64_t nnz, const int32_t *h_indptr, const int32_t *h_indices,
+                                  const double *h_data, int32_t device, void *stream, cy2p_plan **out) {
+    CY2P_REQUIRE(nnz >= 0 && (nnz == 0 || h_data), "null data");
+    std::vector<float> hi((size_t)nnz), lo((size_t)nnz);
+    bool any = false;
+    for (int64_t p = 0; p < nnz; ++p) {
+        hi[p] = (float)h_data[p];
+        lo[p] = (float)(h_data[p] - (double)hi[p]);
+        any |= lo[p] != 0.f;
+    }
+    // (a float64 array whose values are all float32-representable is an ordinary float32 matrix)
+    return plan_build(n, nnz, h_indptr, h_indices, hi.data(), cudaMemcpyHostToDevice, device, (cudaStream_t)stream, out,
+                      any ? lo.data() : nullptr);
+}
+
 int32_t cy2p_plan_destroy(cy2p_plan *plan) {
     if (plan) {
         cudaSetDevice(plan->device);
@@ -377,7 +421,7 @@ int32_t cy2p_cdf_build(const cy2p_plan *plan, int32_t *d_idx, float *d_cum, int3
     CY2P_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
     const int TB = 128;
     count_launch(); cdf_build_kernel<<<(plan->n + TB - 1) / TB, TB, 0, st>>>(plan->n, W, plan->d_indptr, plan->d_indices,
-                                                             plan->d_data, d_idx, d_cum, flag);
+                                                             plan->d_data, plan->d_data_lo, d_idx, d_cum, flag);
     int32_t h = 0;
     cudaError_t e = cudaMemcpyAsync(&h, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

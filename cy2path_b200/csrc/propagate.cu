@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include <type_traits>
 
 namespace cg = cooperative_groups;
 
@@ -632,7 +633,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 spmv_rows(int32_t row_begin, int32_t row_end, const int32_t *__restrict__ t_indptr, const Pair *__restrict__ pairs,
           const T *__restrict__ x, T *__restrict__ y, T *const *__restrict__ peer_out, int32_t npeers,
-          const uint32_t *__restrict__ peer_mask) {
+          const uint32_t *__restrict__ peer_mask, const float *__restrict__ lo = nullptr /* float64 matrix: value = val + lo */) {
     constexpr int G = 8;
     const int lane = threadIdx.x & 31, gl = lane % G;
     const int32_t r = row_begin + (int32_t)((blockIdx.x * (blockDim.x / G)) + threadIdx.x / G);
@@ -641,16 +642,18 @@ spmv_rows(int32_t row_begin, int32_t row_end, const int32_t *__restrict__ t_indp
     T acc = (T)0;
     for (int32_t p0 = beg + gl; p0 < end; p0 += 4 * G) {
         Pair e[4];
-        T xv[4];
+        T xv[4], tv[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int32_t p = p0 + k * G;
             e[k] = p < end ? pairs[p] : Pair{0, 0.f};
+            tv[k] = (T)e[k].val;
+            if (lo != nullptr && p < end) tv[k] += (T)lo[p];
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) xv[k] = (p0 + k * G < end) ? __ldg(x + e[k].src) : (T)0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc = fma((T)e[k].val, xv[k], acc);
+        for (int k = 0; k < 4; ++k) acc = fma(tv[k], xv[k], acc);
     }
 #pragma unroll
     for (int o = G / 2; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -765,6 +768,40 @@ __global__ void sumsq_kernel(int32_t n, const double *__restrict__ v, double *ou
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s = fma(v[i], v[i], s);
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+// One update's eps of a single float64 row, one CTA, fixed summation order (bit-reproducible): used by the float64-
+// matrix single-start path below.
+__global__ void __launch_bounds__(1024)
+eps_row_kernel(int32_t n, const double *__restrict__ y, const double *__restrict__ pi, const double *__restrict__ vv,
+               double *__restrict__ eps_out) {
+    __shared__ double s_uv[32], s_uu[32];
+    double uv = 0.0, uu = 0.0;
+    for (int32_t i = threadIdx.x; i < n; i += 1024) {
+        const double v = y[i];
+        uv = fma(v, pi[i], uv);
+        uu = fma(v, v, uu);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        uv += __shfl_xor_sync(0xffffffffu, uv, o);
+        uu += __shfl_xor_sync(0xffffffffu, uu, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_uv[threadIdx.x >> 5] = uv;
+        s_uu[threadIdx.x >> 5] = uu;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uv = 0.0;
+        uu = 0.0;
+        for (int k = 0; k < 32; ++k) {
+            uv += s_uv[k];
+            uu += s_uu[k];
+        }
+        const double d = 1.0 - uv / sqrt(uu * vv[0]);
+        eps_out[0] = fmin(fmax(d, 0.0), 2.0);
+    }
 }
 
 // eps[i] = clip(1 - uv/sqrt(uu*vv), 0, 2): scipy.spatial.distance.cosine as called at sampling.py:44.
@@ -932,6 +969,32 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
     }
     if (d_history)  // row 0 of the history is the start distribution (sampling.py:39)
         CY2P_CUDA(cudaMemcpyAsync(d_history, d_X0, sizeof(T) * (size_t)n * B, cudaMemcpyDeviceToDevice, st));
+
+    // ---- B == 1 on a float64 matrix (cy2p_plan_create_host_f64): one launch per update with value = hi + lo. scvelo's
+    // matrices are float32 and never come here; this path trades the single-launch kernels below for the exact product
+    // the reference forms with a user-supplied float64 T (sampling.py:40-42). -------------------------------------------
+    if constexpr (std::is_same<T, double>::value) {
+        if (B == 1 && plan->d_t_lo && (!d_history || history_stride == 1)) {
+            const double *src = d_X0;
+            const unsigned grid = (unsigned)((n + 31) / 32);
+            for (int32_t it = 0; it < iters; ++it) {
+                const bool last = it + 1 == iters;
+                // history row h is the iterate BEFORE update h (row 0 = the start, copied above)
+                double *dst = (d_history && !last) ? d_history + (size_t)(it + 1) * n
+                                                   : (last && d_Xfinal ? d_Xfinal : ((it & 1) ? bufA : bufB));
+                count_launch();
+                spmv_rows<double><<<grid, 256, 0, st>>>(0, n, plan->d_t_indptr, plan->d_t_pairs, src, dst, nullptr, 0,
+                                                        nullptr, plan->d_t_lo);
+                if (d_eps) {
+                    count_launch();
+                    eps_row_kernel<<<1, 1024, 0, st>>>(n, dst, d_stationary, vv, d_eps + it);
+                }
+                src = dst;
+            }
+            CY2P_CUDA(cudaGetLastError());
+            return CY2P_OK;
+        }
+    }
 
     // ---- B == 1: all iterations in one launch --------------------------------------------------
     if (B == 1 && (!d_history || history_stride == 1)) {

@@ -417,11 +417,13 @@ spmm_gather_x_multi(int32_t n_rows, int32_t rows_per_item, int32_t nslabs, int32
 }
 
 // ---- small kernels ----------------------------------------------------------------------------------------------
-__global__ void widen_pairs_kernel(int64_t nnz, const Pair *__restrict__ in, PairD *__restrict__ out) {
+// lo != null: the plan holds a float64 matrix as hi + lo (common.cuh); the sum is exact in float64.
+__global__ void widen_pairs_kernel(int64_t nnz, const Pair *__restrict__ in, const float *__restrict__ lo,
+                                   PairD *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nnz) {
         const Pair e = in[i];
-        out[i] = PairD{e.src, 0, (double)e.val};
+        out[i] = PairD{e.src, 0, lo ? (double)e.val + (double)lo[i] : (double)e.val};
     }
 }
 
@@ -573,14 +575,14 @@ static XWs x_ws_layout(const cy2p_plan *plan, int32_t B, int32_t iters, int want
     return w;
 }
 
-static int32_t ensure_pairsD(cy2p_plan *plan, const Pair *src, PairD **dst, cudaStream_t st) {
+static int32_t ensure_pairsD(cy2p_plan *plan, const Pair *src, const float *lo, PairD **dst, cudaStream_t st) {
     if (*dst || !src) return CY2P_OK;
     const size_t bytes = sizeof(PairD) * (size_t)(plan->nnz ? plan->nnz : 1);
     CY2P_CUDA(cudaMalloc((void **)dst, bytes));
     plan->bytes_owned += bytes;
     if (plan->nnz) {
         count_launch();
-        widen_pairs_kernel<<<(unsigned)((plan->nnz + 255) / 256), 256, 0, st>>>(plan->nnz, src, *dst);
+        widen_pairs_kernel<<<(unsigned)((plan->nnz + 255) / 256), 256, 0, st>>>(plan->nnz, src, lo, *dst);
     }
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
@@ -704,10 +706,10 @@ int32_t cy2p_propagate_x(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t 
     const bool reord = plan->reorder_state == 1;
     int32_t rc;
     if (reord) {
-        if ((rc = ensure_pairsD(plan, plan->d_r_pairs_pp, &plan->d_r_pairsD_pp, st)) != CY2P_OK) return rc;
-        if ((rc = ensure_pairsD(plan, plan->d_r_pairs_op, &plan->d_r_pairsD_op, st)) != CY2P_OK) return rc;
+        if ((rc = ensure_pairsD(plan, plan->d_r_pairs_pp, plan->d_r_lo_pp, &plan->d_r_pairsD_pp, st)) != CY2P_OK) return rc;
+        if ((rc = ensure_pairsD(plan, plan->d_r_pairs_op, plan->d_r_lo_op, &plan->d_r_pairsD_op, st)) != CY2P_OK) return rc;
     } else {
-        if ((rc = ensure_pairsD(plan, plan->d_t_pairs, &plan->d_t_pairsD, st)) != CY2P_OK) return rc;
+        if ((rc = ensure_pairsD(plan, plan->d_t_pairs, plan->d_t_lo, &plan->d_t_pairsD, st)) != CY2P_OK) return rc;
     }
     unsigned long long *eps_acc = (unsigned long long *)(ws + w.eps_acc);
     double *scal = (double *)(ws + w.scal);  // [0] fixed-point scale, [1] |stationary|^2

@@ -160,6 +160,11 @@ int32_t ensure_reordered(cy2p_plan *plan, cudaStream_t st) {
     CY2P_CUDA(cudaMemcpyAsync(out_idx.data(), plan->d_indices, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost, st));
     CY2P_CUDA(cudaMemcpyAsync(in_ptr.data(), plan->d_t_indptr, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, st));
     CY2P_CUDA(cudaMemcpyAsync(in_pairs.data(), plan->d_t_pairs, sizeof(Pair) * nnz, cudaMemcpyDeviceToHost, st));
+    std::vector<float> in_lo;  // residuals of a float64 matrix, entry for entry with in_pairs
+    if (plan->d_t_lo) {
+        in_lo.resize(nnz);
+        CY2P_CUDA(cudaMemcpyAsync(in_lo.data(), plan->d_t_lo, sizeof(float) * nnz, cudaMemcpyDeviceToHost, st));
+    }
     CY2P_CUDA(cudaStreamSynchronize(st));
 
     std::vector<int32_t> order;
@@ -180,6 +185,7 @@ int32_t ensure_reordered(cy2p_plan *plan, cudaStream_t st) {
 
     std::vector<int32_t> r_ptr((size_t)n + 1);
     std::vector<Pair> pp(nnz), op(nnz);
+    std::vector<float> lo_pp(in_lo.size()), lo_op(in_lo.size());
     r_ptr[0] = 0;
     for (int32_t q = 0; q < n; ++q) r_ptr[q + 1] = r_ptr[q] + (in_ptr[order[q] + 1] - in_ptr[order[q]]);
     // rows are independent: a few host threads share the permute + per-row sort (95 -> ~25 ms at 1.5 M entries)
@@ -193,7 +199,21 @@ int32_t ensure_reordered(cy2p_plan *plan, cudaStream_t st) {
                 dop[t] = e;  // ascending original source, as in T^T
                 dpp[t] = Pair{pos[e.src], e.val};
             }
-            std::sort(dpp, dpp + len, [](const Pair &a, const Pair &b) { return a.src < b.src; });  // ascending addresses
+            if (in_lo.empty()) {
+                std::sort(dpp, dpp + len, [](const Pair &a, const Pair &b) { return a.src < b.src; });  // ascending addresses
+                continue;
+            }
+            struct Wide { Pair p; float lo; };
+            std::vector<Wide> w((size_t)len);
+            for (int32_t t = 0; t < len; ++t) {
+                lo_op[r_ptr[q] + t] = in_lo[in_ptr[j] + t];
+                w[t] = Wide{dpp[t], in_lo[in_ptr[j] + t]};
+            }
+            std::sort(w.begin(), w.end(), [](const Wide &a, const Wide &b) { return a.p.src < b.p.src; });
+            for (int32_t t = 0; t < len; ++t) {
+                dpp[t] = w[t].p;
+                lo_pp[r_ptr[q] + t] = w[t].lo;
+            }
         }
     };
     {
@@ -263,6 +283,10 @@ int32_t ensure_reordered(cy2p_plan *plan, cudaStream_t st) {
     if (e == cudaSuccess) e = upload((void **)&plan->d_r_indptr, r_ptr.data(), sizeof(int32_t) * ((size_t)n + 1));
     if (e == cudaSuccess) e = upload((void **)&plan->d_r_pairs_pp, pp.data(), sizeof(Pair) * nnz);
     if (e == cudaSuccess) e = upload((void **)&plan->d_r_pairs_op, op.data(), sizeof(Pair) * nnz);
+    if (!in_lo.empty()) {
+        if (e == cudaSuccess) e = upload((void **)&plan->d_r_lo_pp, lo_pp.data(), sizeof(float) * nnz);
+        if (e == cudaSuccess) e = upload((void **)&plan->d_r_lo_op, lo_op.data(), sizeof(float) * nnz);
+    }
     if (!blk_usrc.empty()) {
         if (e == cudaSuccess) e = upload((void **)&plan->d_blk_row, blk_row.data(), sizeof(int32_t) * blk_row.size());
         if (e == cudaSuccess) e = upload((void **)&plan->d_blk_uptr, blk_uptr.data(), sizeof(int32_t) * blk_uptr.size());

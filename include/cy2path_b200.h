@@ -58,6 +58,13 @@ int32_t cy2p_plan_create(int32_t n, int64_t nnz, const int32_t *d_indptr, const 
 /* Same, from host arrays (copies H2D inside). */
 int32_t cy2p_plan_create_host(int32_t n, int64_t nnz, const int32_t *h_indptr, const int32_t *h_indices,
                               const float *h_data, int32_t device, void *stream, cy2p_plan **out);
+/* Same, for a float64 matrix (a user-supplied ``adata.obsp[matrix_key]`` of dtype float64; sampling.py:40-42 then
+ * multiplies in float64 and simulation.py:24-25 accumulates the CDF in float64). Values are held as float32 pairs
+ * hi + lo (48 mantissa bits, 2^-48 relative): cy2p_propagate_f64 with B == 1, cy2p_propagate_x and cy2p_cdf_build use
+ * hi + lo; every other entry point uses hi = float32(value). Values that are all float32-representable give an
+ * ordinary plan. */
+int32_t cy2p_plan_create_host_f64(int32_t n, int64_t nnz, const int32_t *h_indptr, const int32_t *h_indices,
+                                  const double *h_data, int32_t device, void *stream, cy2p_plan **out);
 int32_t cy2p_plan_destroy(cy2p_plan *plan);
 /* info[0]=n info[1]=nnz info[2]=max in-degree info[3]=max out-degree (stored) info[4]=CDF table width W
  * info[5]=device info[6]=locality ordering (0 not built yet, 1 active, -1 rejected) info[7]=bytes of device memory owned */
