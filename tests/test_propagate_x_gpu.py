@@ -245,3 +245,32 @@ def test_config2_full_size_4096_starts_2000_iterations():
     mass = X.sum(0, dtype=np.float64)
     assert np.abs(mass - 1).max() <= 1e-4 and X.min() >= 0
     assert np.isfinite(r["eps"]).all() and r["eps"].min() >= 0 and r["eps"].max() <= 2
+
+
+def test_config4_size_250k_cells_1000_iterations():
+    """BASELINE config 4's graph at full size (250,000 cells, 7.5e6 transitions), one GPU's share of the strong-scaled
+    run at 8 GPUs (512 of the 4,096 starts), all 1,000 updates: four columns against the float64 oracle at the
+    north_star bar, with their eps histories and convergence cuts."""
+    from cy2path_b200.sampling import check_convergence_criteria, propagate_batch
+    from cy2path_b200.synth import batched_starts, knn_velocity_tpm, stationary_by_power
+
+    n = 250_000
+    g = knn_velocity_tpm(n, k=30, seed=4)
+    T = g["T"]
+    B, iters, tol = 512, 1000, 1e-5
+    X0 = batched_starts(T, B, seed=4)
+    stat = stationary_by_power(T, 30)
+    r = propagate_batch(T, X0, iters, stationary=stat, tol=tol)
+    X = r["final"]
+    assert X.shape == (n, B) and X.dtype == np.float32 and r["eps"].shape == (iters, B)
+    cols = [0, 255, 256, 511]
+    ref, eps_ref = _oracle_run(T, X0[:, cols], iters, stat)
+    got = X[:, cols]
+    assert np.abs(got - ref).max() <= MAX_ABS
+    assert _rel_l1_cols(got, ref) <= REL_L1
+    assert np.abs(r["eps"][:, cols] - eps_ref).max() <= 1e-9
+    for j, c in enumerate(cols):
+        cc = check_convergence_criteria(eps_ref[:, j], tol)
+        assert r["convergence"][c] == (cc if (cc is not None and cc < iters) else iters)
+    mass = X.sum(0, dtype=np.float64)
+    assert np.abs(mass - 1).max() <= 1e-4 and X.min() >= 0
