@@ -138,13 +138,15 @@ struct AuxOffsets {
     }
 };
 
-__global__ void __launch_bounds__(512) fhmm_small_forward(int S, int L, int I, int restricted, int KP, int P,
-                                                          const float *__restrict__ theta_pi,
-                                                          const float *__restrict__ theta_w,
-                                                          const float *__restrict__ theta_A, float *__restrict__ small,
-                                                          float *__restrict__ hidden, float *__restrict__ G,
-                                                          float *__restrict__ aux, double *__restrict__ Hlin,
-                                                          double *__restrict__ Apow) {
+// hf_smem != 0: the launch reserved I*S*L more floats of shared memory; H is kept there as float for the time average
+// and the mixing matrix (both used to re-read Hlin from global memory in loops of dependent L2 round trips).
+__global__ void __launch_bounds__(1024) fhmm_small_forward(int S, int L, int I, int restricted, int KP, int P,
+                                                           const float *__restrict__ theta_pi,
+                                                           const float *__restrict__ theta_w,
+                                                           const float *__restrict__ theta_A, float *__restrict__ small,
+                                                           float *__restrict__ hidden, float *__restrict__ G,
+                                                           float *__restrict__ aux, double *__restrict__ Hlin,
+                                                           double *__restrict__ Apow, int hf_smem) {
     const SmallOffsets so(S, L);
     const AuxOffsets ao(S, L);
     float *log_pi = small + so.log_pi, *log_w = small + so.log_w, *log_A = small + so.log_A,
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(512) fhmm_small_forward(int S, int L, int I, i
     float *s_logA = sm;                   // [L][S][S]
     float *s_h = s_logA + L * S * S;      // [2][S][L]
     float *s_logw = s_h + 2 * S * L;      // [L]
+    float *s_amix = s_logw + L;           // [S][S]
     const int tid = threadIdx.x, nt = blockDim.x;
 
     // log_softmax(theta_pi, dim=0): per lineage l over states
@@ -195,11 +198,12 @@ __global__ void __launch_bounds__(512) fhmm_small_forward(int S, int L, int I, i
         float z = 0.f;
         for (int l = 0; l < L; ++l) z += expf(s_logA[l * S * S + e] + s_logw[l] - m);
         log_Amix[e] = m + logf(z);
+        s_amix[e] = m + logf(z);
     }
     __syncthreads();
     if (tid == 0) {
         float d = 0.f;
-        for (int s = 0; s < S; ++s) d += log_Amix[s * S + s];
+        for (int s = 0; s < S; ++s) d += s_amix[s * S + s];
         aux[ao.sparsity] = -d / (float)S;
     }
 
@@ -213,9 +217,10 @@ __global__ void __launch_bounds__(512) fhmm_small_forward(int S, int L, int I, i
     const int SL = S * L, SS = S * S;
     const int warp = tid >> 5, lane = tid & 31;
     const int NB = (I + P - 1) / P;
-    double *s_pow = reinterpret_cast<double *>(sm + ((L * SS + 2 * SL + L + 1) & ~1));  // [P][L][S][S]: A^(j+1)
+    double *s_pow = reinterpret_cast<double *>(sm + ((L * SS + 2 * SL + L + SS + 1) & ~1));  // [P][L][S][S]: A^(j+1)
     double *s_X = s_pow + (size_t)P * L * SS;                                         // [NB][S][L] (unused if P == 1)
     double *s_part = s_X + (P > 1 ? (size_t)NB * SL : 0);                              // [blockDim]
+    float *s_Hf = reinterpret_cast<float *>(s_part + nt);                              // [I][S][L] when hf_smem
     for (int i = tid; i < L * SS; i += nt) {
         const double a = exp((double)s_logA[i]);
         s_pow[i] = a;
@@ -263,9 +268,14 @@ __global__ void __launch_bounds__(512) fhmm_small_forward(int S, int L, int I, i
     // t, so the index arithmetic of the inner loop is additions only
     const int l3_groups = nt / SL;
     const int l3_e = tid % SL, l3_sp = l3_e / L, l3_l = l3_e % L;
-    for (int t = tid / SL; l3_groups > 0 && tid < l3_groups * SL && t < I; t += l3_groups) {
+    int l3_b = (tid / SL) / P, l3_j = (tid / SL) - l3_b * P;
+    for (int t = tid / SL; l3_groups > 0 && tid < l3_groups * SL && t < I; t += l3_groups, l3_j += l3_groups) {
         const int i = t * SL + l3_e, sp = l3_sp, l = l3_l;
-        const int b = t / P, j = t - b * P;
+        while (l3_j >= P) {
+            l3_j -= P;
+            ++l3_b;
+        }
+        const int b = l3_b, j = l3_j;
         double h;
         if (P == 1) {
             h = Hlin[i];  // level 2 already produced every step
@@ -284,6 +294,7 @@ __global__ void __launch_bounds__(512) fhmm_small_forward(int S, int L, int I, i
             h = a0 + a1;
         }
         if (P > 1) Hlin[i] = h;
+        if (hf_smem) s_Hf[i] = (float)h;
         hidden[i] = h > 1e-30 ? logf((float)h) : (float)log(h);
     }
     __syncthreads();
@@ -293,7 +304,11 @@ __global__ void __launch_bounds__(512) fhmm_small_forward(int S, int L, int I, i
         const int gidx = tid / SL, e = tid % SL;
         if (gidx < groups) {
             double acc = 0.0;
-            for (int t = gidx; t < I; t += groups) acc += Hlin[(size_t)t * SL + e];
+            if (hf_smem) {
+                for (int t = gidx; t < I; t += groups) acc += (double)s_Hf[(size_t)t * SL + e];
+            } else {
+                for (int t = gidx; t < I; t += groups) acc += Hlin[(size_t)t * SL + e];
+            }
             s_part[gidx * SL + e] = acc;
         }
         __syncthreads();
@@ -313,14 +328,19 @@ __global__ void __launch_bounds__(512) fhmm_small_forward(int S, int L, int I, i
         for (int i = tid; i < I * KP; i += nt) {
             const int t = i / KP, k = i % KP;
             float g = 0.f;
-            if (k < S)
-                for (int ll = 0; ll < L; ++ll) g += (float)Hlin[(size_t)t * SL + k * L + ll] * s_wf[ll];
+            if (k < S) {
+                if (hf_smem) {
+                    for (int ll = 0; ll < L; ++ll) g += s_Hf[(size_t)t * SL + k * L + ll] * s_wf[ll];
+                } else {
+                    for (int ll = 0; ll < L; ++ll) g += (float)Hlin[(size_t)t * SL + k * L + ll] * s_wf[ll];
+                }
+            }
             G[i] = g;
         }
     } else {
         for (int i = tid; i < I * KP; i += nt) {
             const int t = i / KP, k = i % KP;
-            G[i] = k < SL ? (float)Hlin[(size_t)t * SL + k] * s_wf[k % L] : 0.f;
+            G[i] = k < SL ? (hf_smem ? s_Hf[(size_t)t * SL + k] : (float)Hlin[(size_t)t * SL + k]) * s_wf[k % L] : 0.f;
         }
     }
     __syncthreads();
@@ -1442,6 +1462,224 @@ fhmm_small_backward(int S, int L, int I, int P, int restricted, int K, const flo
 }
 
 // --------------------------------------------------------------------------------------------------
+// fhmm_bwd_local + fhmm_small_backward as ONE CTA of 1,024 threads that works out of shared memory. The two kernels
+// above walk R, H and gG in global memory inside loops whose iterations each wait for an L2 round trip (24 + 104 us at
+// config 3 with every SM but one idle); here A^1..A^P, R (-> gH), H, gG and the node-level scalars are staged once with
+// all loads in flight, and every later phase reads shared memory:
+//   0  stage                      1  R_t = c_t + A R_{t+1} inside the blocks (a warp per (block, lineage))
+//   2  Y_b chain over the blocks  3  gH_t = R_t + A^{e_b - t} Y_b in place
+//   4  g_pi                       5  gA = sum_t H_t (x) gH_{t+1} (the t range split over the idle threads, fixed order)
+//   6  softmax Jacobians of A, w and the 8 reported scalars
+// Used when fused_bwd_smem() fits (config 3: 224 KB); larger shapes keep the two-kernel path.
+__host__ __device__ inline size_t fused_bwd_floats(int S, int L, int I, int P, int K, int nt) {
+    const size_t SL = (size_t)S * L, NB = (size_t)(I + P - 1) / P;
+    return (size_t)P * L * S * (S | 1) + 2 * (size_t)I * SL + ((size_t)K == SL ? 0 : (size_t)I * K) + NB * SL +
+           (size_t)L * S * S + SL + 2 * (size_t)L + S + (size_t)nt;
+}
+
+__global__ void __launch_bounds__(1024)
+fhmm_backward_fused(int S, int L, int I, int P, int restricted, int K, const float *__restrict__ small,
+                    const double *__restrict__ Hlin, const double *__restrict__ Apow, const float *__restrict__ aux,
+                    const float *__restrict__ gG, const double *__restrict__ scal, float w_sparse, float w_excl,
+                    float w_orth, float w_tpm, float *__restrict__ g_pi, float *__restrict__ g_w,
+                    float *__restrict__ g_A, float *__restrict__ terms) {
+    const SmallOffsets so(S, L);
+    const AuxOffsets ao(S, L);
+    const ScalarOffsets sc(S, L, K);
+    const float *log_pi = small + so.log_pi, *log_w = small + so.log_w, *log_Amix = small + so.log_Amix;
+    extern __shared__ double smd[];
+    const int SL = S * L, SS = S * S, SP = S | 1, LSS = L * SS;
+    const int NB = (I + P - 1) / P;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+    double *s_scal = smd;                                            // [sc.total]
+    float *s_pow = reinterpret_cast<float *>(s_scal + ((sc.total + 1) & ~1));  // [P][L][S][SP]: A^(j+1), rows padded
+    float *s_R = s_pow + (size_t)P * L * S * SP;                     // [I][SL]: R, then gH
+    float *s_H = s_R + (size_t)I * SL;                               // [I][SL]
+    float *s_gG = (K == SL) ? s_R : s_H + (size_t)I * SL;            // [I][K] (in place of R when the indices coincide)
+    float *s_Y = s_H + (size_t)I * SL + (K == SL ? 0 : (size_t)I * K);  // [NB][SL]
+    float *s_gA = s_Y + (size_t)NB * SL;                             // [L][S][S]
+    float *s_base = s_gA + LSS;                                      // [SL]
+    float *s_w = s_base + SL;                                        // [L]
+    float *s_gw = s_w + L;                                           // [L]
+    float *s_amd = s_gw + L;                                         // [S]: A_mix[s,s]
+    float *s_red = s_amd + S;                                        // [nt]
+
+    // ---- 0: stage
+#pragma unroll 4
+    for (int i = tid; i < sc.total; i += nt) s_scal[i] = scal[i];
+#pragma unroll 4
+    for (int i = tid; i < P * LSS; i += nt) s_pow[(i / S) * SP + i % S] = (float)Apow[i];
+#pragma unroll 8
+    for (int i = tid; i < I * SL; i += nt) s_H[i] = (float)Hlin[i];
+#pragma unroll 8
+    for (int i = tid; i < I * K; i += nt) s_gG[i] = gG[i];
+    for (int i = tid; i < L; i += nt) {
+        s_w[i] = expf(log_w[i]);
+        s_gw[i] = 0.f;
+    }
+    for (int i = tid; i < S; i += nt) s_amd[i] = expf(log_Amix[i * S + i]);
+    for (int i = tid; i < SL; i += nt)
+        s_base[i] = (float)scal[sc.glogC + i] / ((float)I * fmaxf(aux[ao.Hbar + i], FLT_MIN));
+    __syncthreads();
+
+    // ---- 1: R inside the blocks, gw_l = sum_{t,s} gG_t[s,l] H_t[s,l]
+    for (int task = warp; task < NB * L; task += nwarps) {
+        const int b = task / L, l = task - b * L;
+        const bool on = lane < S;
+        const int sl = on ? lane * L + l : 0;
+        const float base = on ? s_base[sl] : 0.f, wl = s_w[l];
+        const float *Arow = s_pow + (size_t)(l * S + (on ? lane : 0)) * SP;  // A^1
+        const int kidx = restricted ? (on ? lane : 0) : sl;
+        const int t_lo = b * P, t_hi = min(I, t_lo + P);
+        float r_next = 0.f, gw_part = 0.f;
+        for (int t = t_hi - 1; t >= t_lo; --t) {
+            const float gg = on ? s_gG[(size_t)t * K + kidx] : 0.f;
+            if (on) gw_part = fmaf(gg, s_H[(size_t)t * SL + sl], gw_part);
+            float a0 = on ? fmaf(wl, gg, base) : 0.f, a1 = 0.f;
+            if (t + 1 < t_hi) {
+                int sp = 0;
+                for (; sp + 1 < S; sp += 2) {
+                    const float n0 = __shfl_sync(0xffffffffu, r_next, sp), n1 = __shfl_sync(0xffffffffu, r_next, sp + 1);
+                    a0 = fmaf(Arow[sp], n0, a0);
+                    a1 = fmaf(Arow[sp + 1], n1, a1);
+                }
+                if (sp < S) a0 = fmaf(Arow[sp], __shfl_sync(0xffffffffu, r_next, sp), a0);
+            }
+            r_next = on ? a0 + a1 : 0.f;
+            __syncwarp();  // K == SL: every lane has read its gG entry before the row is overwritten
+            if (on) s_R[(size_t)t * SL + sl] = r_next;
+        }
+        gw_part = warp_sum(gw_part);
+        if (lane == 0) atomicAdd(&s_gw[l], gw_part);
+    }
+    __syncthreads();
+
+    // ---- 2: Y_b = gH at the first step after block b, one warp per lineage
+    if (warp < L) {
+        const int l = warp;
+        const bool on = lane < S;
+        const int sl = on ? lane * L + l : 0;
+        const float *AProw = s_pow + ((size_t)(P - 1) * L * S + (size_t)l * S + (on ? lane : 0)) * SP;
+        float y = 0.f;
+        for (int b = NB - 1; b >= 0; --b) {
+            if (on) s_Y[(size_t)b * SL + sl] = y;
+            if (b == 0) break;
+            const int span = min(I, (b + 1) * P) - b * P;
+            const float *Arow = (span == P) ? AProw
+                                            : s_pow + ((size_t)(span - 1) * L * S + (size_t)l * S + (on ? lane : 0)) * SP;
+            float a0 = on ? s_R[(size_t)(b * P) * SL + sl] : 0.f, a1 = 0.f;
+            int sp = 0;
+            for (; sp + 1 < S; sp += 2) {
+                const float n0 = __shfl_sync(0xffffffffu, y, sp), n1 = __shfl_sync(0xffffffffu, y, sp + 1);
+                a0 = fmaf(Arow[sp], n0, a0);
+                a1 = fmaf(Arow[sp + 1], n1, a1);
+            }
+            if (sp < S) a0 = fmaf(Arow[sp], __shfl_sync(0xffffffffu, y, sp), a0);
+            y = on ? a0 + a1 : 0.f;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3: gH_t = R_t + A^{e_b - t} Y_b in place; a thread keeps one (s, l) and strides over t
+    {
+        const int groups = nt / SL;  // SL <= 512
+        const int gidx = tid / SL, e = tid - gidx * SL, s0 = e / L, l = e - s0 * L;
+        if (gidx < groups) {
+            int b = gidx / P, e_b = min(I, (b + 1) * P);
+            for (int t = gidx; t < I; t += groups) {
+                while (t >= e_b) {
+                    ++b;
+                    e_b = min(I, (b + 1) * P);
+                }
+                const int pw = e_b - t;  // >= 1
+                const float *Arow = s_pow + ((size_t)(pw - 1) * L * S + (size_t)l * S + s0) * SP;
+                const float *Y = s_Y + (size_t)b * SL + l;
+                float a0 = s_R[(size_t)t * SL + e], a1 = 0.f;
+                int sp = 0;
+                for (; sp + 1 < S; sp += 2) {
+                    a0 = fmaf(Arow[sp], Y[sp * L], a0);
+                    a1 = fmaf(Arow[sp + 1], Y[(sp + 1) * L], a1);
+                }
+                if (sp < S) a0 = fmaf(Arow[sp], Y[sp * L], a0);
+                s_R[(size_t)t * SL + e] = a0 + a1;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 4: theta_pi: glogpi = pi * gH_0, softmax over s (per lineage)
+    if (warp < L) {
+        const int l = warp;
+        const bool on = lane < S;
+        const float pi = on ? expf(log_pi[lane * L + l]) : 0.f;
+        const float pg = on ? pi * s_R[lane * L + l] : 0.f;
+        const float dot = warp_sum(pg);
+        if (on) g_pi[lane * L + l] = pg - pi * dot;
+    }
+    // ---- 5: gA[l,s,s'] = sum_{t=0}^{I-2} H_t[s,l] gH_{t+1}[s',l]; `parts` slices of t per output, added in order
+    {
+        const int parts = max(1, min(8, nt / LSS));
+        const int T1 = I - 1, per = (T1 + parts - 1) / parts;
+        for (int base_o = 0; base_o < LSS; base_o += (parts > 1 ? LSS : nt)) {
+            // parts > 1: one sweep (LSS * parts <= nt); parts == 1: outputs strided over the threads
+            const int part = parts > 1 ? tid / LSS : 0;
+            const int o = parts > 1 ? tid - part * LSS : base_o + tid;
+            float a0 = 0.f, a1 = 0.f;
+            const bool live = part < parts && o < LSS;
+            if (live) {
+                const int l = o / SS, s0 = (o / S) % S, sp = o % S;
+                const float *h = s_H + s0 * L + l, *g = s_R + SL + sp * L + l;
+                const int t0 = part * per, t1 = min(T1, t0 + per);
+                int t = t0;
+                for (; t + 1 < t1; t += 2) {
+                    a0 = fmaf(h[(size_t)t * SL], g[(size_t)t * SL], a0);
+                    a1 = fmaf(h[(size_t)(t + 1) * SL], g[(size_t)(t + 1) * SL], a1);
+                }
+                if (t < t1) a0 = fmaf(h[(size_t)t * SL], g[(size_t)t * SL], a0);
+            }
+            if (parts > 1) {
+                s_red[tid] = a0 + a1;
+                __syncthreads();
+                if (tid < LSS) {
+                    float a = 0.f;
+                    for (int q = 0; q < parts; ++q) a += s_red[q * LSS + tid];
+                    s_gA[tid] = a;
+                }
+            } else if (live) {
+                s_gA[o] = a0 + a1;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 6: theta_A: glogA = A*gA + sparsity part on the diagonal, softmax over s'; theta_w; the reported scalars
+    for (int r = tid; r < L * S; r += nt) {
+        const int l = r / S, s0 = r % S;
+        const float *Ar = s_pow + (size_t)r * SP;  // A^1
+        const float diag = -w_sparse / (float)S * s_w[l] * Ar[s0] / s_amd[s0];
+        float sum = 0.f;
+        for (int sp = 0; sp < S; ++sp) sum += Ar[sp] * s_gA[(size_t)r * S + sp] + (sp == s0 ? diag : 0.f);
+        for (int sp = 0; sp < S; ++sp) {
+            const float gl = Ar[sp] * s_gA[(size_t)r * S + sp] + (sp == s0 ? diag : 0.f);
+            g_A[(size_t)r * S + sp] = gl - Ar[sp] * sum;
+        }
+    }
+    if (tid == 0) {
+        float glw[kMaxL], sum = 0.f;
+        for (int l = 0; l < L; ++l) {
+            float g = s_w[l] * s_gw[l];
+            for (int s0 = 0; s0 < S; ++s0) {
+                g += (float)s_scal[sc.glogC + s0 * L + l];
+                g += -w_sparse / (float)S * s_w[l] * s_pow[(size_t)(l * S + s0) * SP + s0] / s_amd[s0];
+            }
+            glw[l] = g;
+            sum += g;
+        }
+        for (int l = 0; l < L; ++l) g_w[l] = glw[l] - s_w[l] * sum;
+        write_terms(S, L, K, s_scal, aux[ao.sparsity], w_sparse, w_excl, w_orth, w_tpm, terms);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // Decoders: filtering / smoothing / viterbi (reference _FHMM.py:153-281). All three reduce to
 //   Bmat[t,k] = lse_n(log D[t,n] + logE[k,n]) = log sum_n D[t,n] E[k,n]     (a dense [I x N].[N x K] contraction)
 // followed by S x L recurrences in the log domain, written as the reference writes them (including its quirks:
@@ -1915,8 +2153,8 @@ int choose_block(int S, int L, int I, size_t *smem_fwd, size_t *smem_bwd) {
     while ((P + 1) * (P + 1) <= I) ++P;
     for (;; --P) {
         const size_t NB = (size_t)(I + P - 1) / P;
-        const size_t f = sizeof(float) * (size_t)((L * S * S + 2 * S * L + L + 1) & ~1) +
-                         sizeof(double) * ((size_t)P * L * S * S + (P > 1 ? NB * S * L : 0) + 512);
+        const size_t f = sizeof(float) * (size_t)((L * S * S + 2 * S * L + L + S * S + 1) & ~1) +
+                         sizeof(double) * ((size_t)P * L * S * S + (P > 1 ? NB * S * L : 0) + 1024);
         const size_t b = sizeof(float) * ((size_t)P * L * S * (S | 1) + (size_t)L * S * S + NB * S * L + 2 * L + 512);
         if ((f <= budget && b <= budget) || P == 1) {
             *smem_fwd = f;
@@ -2128,6 +2366,37 @@ int32_t check_dims(int S, int L, int N, int I, int restricted) {
     return CY2P_OK;
 }
 
+// Backward of the hidden recurrence: the fused shared-memory kernel when its staging fits one CTA, else the two-kernel
+// path. CY2P_FHMM_FUSED_BWD=0 forces the latter (measurement).
+int32_t launch_hidden_backward(int S, int L, int I, int P, int restricted, int K, const float *small,
+                               const double *Hlin, const double *Apow, const float *aux, const float *gG,
+                               const double *scal, float w_sparse, float w_excl, float w_orth, float w_tpm, float *gH,
+                               float *g_pi, float *g_w, float *g_A, float *terms, float *gwacc, size_t smem_local,
+                               size_t smem_bwd, cudaStream_t st) {
+    const ScalarOffsets sc(S, L, K);
+    const int nt = 1024;
+    const size_t fused = sizeof(double) * (size_t)((sc.total + 1) & ~1) + sizeof(float) * fused_bwd_floats(S, L, I, P, K, nt);
+    if (fused <= 227 * 1024 && env_flag("CY2P_FHMM_FUSED_BWD", 1)) {
+        CY2P_CUDA(cudaFuncSetAttribute(fhmm_backward_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused));
+        count_launch();
+        fhmm_backward_fused<<<1, nt, fused, st>>>(S, L, I, P, restricted, K, small, Hlin, Apow, aux, gG, scal, w_sparse,
+                                                  w_excl, w_orth, w_tpm, g_pi, g_w, g_A, terms);
+        CY2P_CUDA(cudaGetLastError());
+        return CY2P_OK;
+    }
+    const int NB = (I + P - 1) / P;
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_local));
+    CY2P_CUDA(cudaMemsetAsync(gwacc, 0, sizeof(float) * kMaxL, st));
+    count_launch();
+    fhmm_bwd_local<<<NB, L * 32, smem_local, st>>>(S, L, I, P, restricted, K, small, aux, gG, scal, gH, Hlin, gwacc);
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bwd));
+    count_launch();
+    fhmm_small_backward<<<1, 512, smem_bwd, st>>>(S, L, I, P, restricted, K, small, Hlin, Apow, aux, gG, scal, w_sparse,
+                                                  w_excl, w_orth, w_tpm, gH, g_pi, g_w, g_A, terms, gwacc);
+    CY2P_CUDA(cudaGetLastError());
+    return CY2P_OK;
+}
+
 // forward pieces shared by cy2p_fhmm_forward and cy2p_fhmm_loss_grad
 int32_t run_emission(int K, int N, const float *theta_E, const FhmmWs &w, char *ws, cudaStream_t st) {
     float *logE = (float *)(ws + w.logE);
@@ -2147,12 +2416,15 @@ int32_t run_small_forward(int S, int L, int I, int restricted, const float *thet
         set_error("model too large for the one-CTA recurrence kernels (S=%d, L=%d, I=%d)", S, L, I);
         return CY2P_ERR_INVALID_ARG;
     }
-    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_fwd));
+    const size_t hf_bytes = sizeof(float) * (size_t)I * S * L;  // float copy of H in shared memory when it fits
+    const int hf = (w.smem_fwd + hf_bytes <= 227 * 1024 && env_flag("CY2P_FHMM_HF_SMEM", 1)) ? 1 : 0;
+    const size_t smem = w.smem_fwd + (hf ? hf_bytes : 0);
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     count_launch();
-    fhmm_small_forward<<<1, 512, w.smem_fwd, st>>>(S, L, I, restricted, w.KP, w.P, theta_pi, theta_w, theta_A,
-                                                   (float *)(ws + w.small), (float *)(ws + w.hidden),
-                                                   (float *)(ws + w.G), (float *)(ws + w.aux), (double *)(ws + w.Hlin),
-                                                   (double *)(ws + w.Apow));
+    fhmm_small_forward<<<1, 1024, smem, st>>>(S, L, I, restricted, w.KP, w.P, theta_pi, theta_w, theta_A,
+                                              (float *)(ws + w.small), (float *)(ws + w.hidden), (float *)(ws + w.G),
+                                              (float *)(ws + w.aux), (double *)(ws + w.Hlin), (double *)(ws + w.Apow),
+                                              hf);
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }
@@ -2216,12 +2488,15 @@ int32_t lssm_run_forward(int S, int L, int Le, int N, int I, int restricted, con
         return CY2P_ERR_INVALID_ARG;
     }
     CY2P_CUDA(cudaMemsetAsync(ws + w.zero, 0, sizeof(float) * 4, st));  // theta_w of the single lineage
-    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_fwd1));
+    const size_t hf_bytes = sizeof(float) * (size_t)I * S;
+    const int hf = (w.smem_fwd1 + hf_bytes <= 227 * 1024 && env_flag("CY2P_FHMM_HF_SMEM", 1)) ? 1 : 0;
+    const size_t smem1 = w.smem_fwd1 + (hf ? hf_bytes : 0);
+    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     count_launch();
-    fhmm_small_forward<<<1, 512, w.smem_fwd1, st>>>(S, 1, I, 1, w.KP1, w.P1, theta_pi, (const float *)(ws + w.zero),
-                                                    theta_A, (float *)(ws + w.small1), (float *)(ws + w.f.hidden),
-                                                    (float *)(ws + w.G1), (float *)(ws + w.aux1),
-                                                    (double *)(ws + w.f.Hlin), (double *)(ws + w.Apow1));
+    fhmm_small_forward<<<1, 1024, smem1, st>>>(S, 1, I, 1, w.KP1, w.P1, theta_pi, (const float *)(ws + w.zero), theta_A,
+                                               (float *)(ws + w.small1), (float *)(ws + w.f.hidden),
+                                               (float *)(ws + w.G1), (float *)(ws + w.aux1), (double *)(ws + w.f.Hlin),
+                                               (double *)(ws + w.Apow1), hf);
     count_launch();
     lssm_mix_forward<<<1, 512, 0, st>>>(S, L, I, restricted, w.f.KP, prenorm, theta_w, (const float *)(ws + w.small1),
                                         (const float *)(ws + w.aux1), (const double *)(ws + w.f.Hlin),
@@ -2278,22 +2553,12 @@ int32_t lssm_loss_core(cy2p_plan *plan, int S, int L, int Le, int N, int I, int 
     lssm_glue_backward<<<S, 256, 0, st>>>(S, L, I, restricted, K, raw, (const float *)(ws + w.lsmall),
                                           (const double *)(ws + w.f.Hlin), (const float *)(ws + w.f.gG), scal, aux,
                                           w_sparse, w_excl, w_orth, w_tpm, (float *)(ws + w.gG1), scal1, d_gw, d_terms);
-    const int NB = (I + w.P1 - 1) / w.P1;
-    CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_local1));
-    count_launch();
-    CY2P_CUDA(cudaMemsetAsync(ws + w.f.gwacc, 0, sizeof(float) * kMaxL, st));
-    fhmm_bwd_local<<<NB, 32, w.smem_local1, st>>>(S, 1, I, w.P1, 1, S, (const float *)(ws + w.small1),
-                                                  (const float *)(ws + w.aux1), (const float *)(ws + w.gG1), scal1,
-                                                  (float *)(ws + w.f.gH), (const double *)(ws + w.f.Hlin),
-                                                  (float *)(ws + w.f.gwacc));
-    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bwd1));
     float *tmp = (float *)(ws + w.tmp);
-    count_launch();
-    fhmm_small_backward<<<1, 512, w.smem_bwd1, st>>>(S, 1, I, w.P1, 1, S, (const float *)(ws + w.small1),
-                                                     (const double *)(ws + w.f.Hlin), (const double *)(ws + w.Apow1),
-                                                     (const float *)(ws + w.aux1), (const float *)(ws + w.gG1), scal1,
-                                                     w_sparse, 0.f, 0.f, 0.f, (float *)(ws + w.f.gH), d_gpi, tmp,
-                                                     d_gA, tmp + 4, (const float *)(ws + w.f.gwacc));
+    rc = launch_hidden_backward(S, 1, I, w.P1, 1, S, (const float *)(ws + w.small1), (const double *)(ws + w.f.Hlin),
+                                (const double *)(ws + w.Apow1), (const float *)(ws + w.aux1),
+                                (const float *)(ws + w.gG1), scal1, w_sparse, 0.f, 0.f, 0.f, (float *)(ws + w.f.gH),
+                                d_gpi, tmp, d_gA, tmp + 4, (float *)(ws + w.f.gwacc), w.smem_local1, w.smem_bwd1, st);
+    if (rc) return rc;
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }
@@ -2508,21 +2773,12 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
                                                                                        d_gE);
     // small backward
     if (dg_on_side) CY2P_CUDA(cudaStreamWaitEvent(st, ev[5], 0));  // dG (side stream) is complete
-    const int NB = (I + w.P - 1) / w.P;
-    CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_local));
-    count_launch();
-    CY2P_CUDA(cudaMemsetAsync(ws + w.gwacc, 0, sizeof(float) * kMaxL, st));
-    fhmm_bwd_local<<<NB, L * 32, w.smem_local, st>>>(S, L, I, w.P, restricted, K, (const float *)(ws + w.small),
-                                                     (const float *)(ws + w.aux), (const float *)(ws + w.gG), scal,
-                                                     (float *)(ws + w.gH), (const double *)(ws + w.Hlin),
-                                                     (float *)(ws + w.gwacc));
-    CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bwd));
-    count_launch();
-    fhmm_small_backward<<<1, 512, w.smem_bwd, st>>>(S, L, I, w.P, restricted, K, (const float *)(ws + w.small),
-                                                    (const double *)(ws + w.Hlin), (const double *)(ws + w.Apow),
-                                                    (const float *)(ws + w.aux), (const float *)(ws + w.gG), scal,
-                                                    w_sparse, w_excl, w_orth, w_tpm, (float *)(ws + w.gH), d_gpi, d_gw,
-                                                    d_gA, d_terms, (const float *)(ws + w.gwacc));
+    rc = launch_hidden_backward(S, L, I, w.P, restricted, K, (const float *)(ws + w.small),
+                                (const double *)(ws + w.Hlin), (const double *)(ws + w.Apow),
+                                (const float *)(ws + w.aux), (const float *)(ws + w.gG), scal, w_sparse, w_excl, w_orth,
+                                w_tpm, (float *)(ws + w.gH), d_gpi, d_gw, d_gA, d_terms, (float *)(ws + w.gwacc),
+                                w.smem_local, w.smem_bwd, st);
+    if (rc) return rc;
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }

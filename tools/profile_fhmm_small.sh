@@ -7,8 +7,8 @@ OUT=gpurun_out/r02
 mkdir -p $OUT
 CMD="python tools/bench_fhmm_mma.py --only restricted_mma_serial --reps 3"
 $CMD > $OUT/fhmm_small_plain_$TAG.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:'fhmm_small_forward|fhmm_small_backward|fhmm_bwd_local' -s 3 -c 3 -f \
+ncu --set full --warp-sampling-interval 0 --clock-control none --import-source on -k regex:"fhmm_small_forward|fhmm_backward_fused" -s 2 -c 2 -f \
     -o $OUT/fhmm_small_$TAG $CMD > $OUT/fhmm_small_ncu_$TAG.log 2>&1
 ncu -i $OUT/fhmm_small_$TAG.ncu-rep --page raw --csv > $OUT/fhmm_small_${TAG}_raw.csv 2>/dev/null
-ncu -i $OUT/fhmm_small_$TAG.ncu-rep --page source --csv --print-source cuda > $OUT/fhmm_small_${TAG}_source.csv 2>/dev/null
+ncu -i $OUT/fhmm_small_$TAG.ncu-rep --page source --csv > $OUT/fhmm_small_${TAG}_source.csv 2>/dev/null
 ls -la $OUT | tail -8
