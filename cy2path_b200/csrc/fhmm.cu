@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(1024) fhmm_small_forward(int S, int L, int I, 
                                                            const float *__restrict__ theta_A, float *__restrict__ small,
                                                            float *__restrict__ hidden, float *__restrict__ G,
                                                            float *__restrict__ aux, double *__restrict__ Hlin,
-                                                           double *__restrict__ Apow, int hf_smem) {
+                                                           double *__restrict__ Apow, int hf_smem,
+                                                           double *__restrict__ Xblk, int *__restrict__ tickets) {
     const SmallOffsets so(S, L);
     const AuxOffsets ao(S, L);
     float *log_pi = small + so.log_pi, *log_w = small + so.log_w, *log_A = small + so.log_A,
@@ -158,36 +159,44 @@ __global__ void __launch_bounds__(1024) fhmm_small_forward(int S, int L, int I, 
     float *s_amix = s_logw + L;           // [S][S]
     const int tid = threadIdx.x, nt = blockDim.x;
 
+    // the three raw parameter blocks come in with one sweep of independent loads; the softmaxes then run out of shared
+    // memory (their max / sum loops would otherwise wait for one L2 round trip per element)
+    for (int i = tid; i < L * S * S; i += nt) s_logA[i] = theta_A[i];
+    for (int i = tid; i < S * L; i += nt) s_h[i] = theta_pi[i];
+    for (int i = tid; i < L; i += nt) s_logw[i] = theta_w[i];
+    __syncthreads();
     // log_softmax(theta_pi, dim=0): per lineage l over states
     for (int l = tid; l < L; l += nt) {
         float m = -INFINITY;
-        for (int s = 0; s < S; ++s) m = fmaxf(m, theta_pi[s * L + l]);
+        for (int s = 0; s < S; ++s) m = fmaxf(m, s_h[s * L + l]);
         float z = 0.f;
-        for (int s = 0; s < S; ++s) z += expf(theta_pi[s * L + l] - m);
+        for (int s = 0; s < S; ++s) z += expf(s_h[s * L + l] - m);
         const float lse = m + logf(z);
-        for (int s = 0; s < S; ++s) log_pi[s * L + l] = theta_pi[s * L + l] - lse;
+        for (int s = 0; s < S; ++s) log_pi[s * L + l] = s_h[s * L + l] - lse;
     }
-    if (tid == 0) {
+    if (tid == 32) {  // (a lane of the second warp: the first is busy with theta_pi)
         float m = -INFINITY;
-        for (int l = 0; l < L; ++l) m = fmaxf(m, theta_w[l]);
+        for (int l = 0; l < L; ++l) m = fmaxf(m, s_logw[l]);
         float z = 0.f;
-        for (int l = 0; l < L; ++l) z += expf(theta_w[l] - m);
+        for (int l = 0; l < L; ++l) z += expf(s_logw[l] - m);
         const float lse = m + logf(z);
         for (int l = 0; l < L; ++l) {
-            log_w[l] = theta_w[l] - lse;
-            s_logw[l] = theta_w[l] - lse;
+            const float v = s_logw[l] - lse;
+            log_w[l] = v;
+            s_logw[l] = v;
         }
     }
-    for (int r = tid; r < L * S; r += nt) {  // rows (l, s) over destination state
-        const float *x = theta_A + (size_t)r * S;
+    for (int r = nt - 1 - tid; r < L * S; r += nt) {  // rows (l, s) over destination state, from the far end of the CTA
+        float *x = s_logA + (size_t)r * S;
         float m = -INFINITY;
         for (int j = 0; j < S; ++j) m = fmaxf(m, x[j]);
         float z = 0.f;
         for (int j = 0; j < S; ++j) z += expf(x[j] - m);
         const float lse = m + logf(z);
         for (int j = 0; j < S; ++j) {
-            log_A[(size_t)r * S + j] = x[j] - lse;
-            s_logA[r * S + j] = x[j] - lse;
+            const float v = x[j] - lse;
+            log_A[(size_t)r * S + j] = v;
+            x[j] = v;
         }
     }
     __syncthreads();
@@ -263,6 +272,11 @@ __global__ void __launch_bounds__(1024) fhmm_small_forward(int S, int L, int I, 
         }
     }
     __syncthreads();
+    if (Xblk != nullptr) {  // split path (P > 1): level 3 and everything after it run as fhmm_forward_expand, one CTA per block
+        for (int i = tid; i < NB * SL; i += nt) Xblk[i] = s_X[i];
+        if (tid < 4) tickets[tid] = 0;  // last-CTA tickets of the three multi-CTA kernels that follow in this call
+        return;
+    }
     // level 3 + hidden = log H
     // a thread keeps one (state, lineage) element when the block is a multiple of S*L threads wide and strides over
     // t, so the index arithmetic of the inner loop is additions only
@@ -348,6 +362,127 @@ __global__ void __launch_bounds__(1024) fhmm_small_forward(int S, int L, int I, 
     float *s_logC = s_h;
     for (int i = tid; i < SL; i += nt) s_logC[i] = aux[ao.logC + i];
     __syncthreads();
+    for (int s0 = tid; s0 < S; s0 += nt) {
+        float m = -INFINITY;
+        for (int ll = 0; ll < L; ++ll) m = fmaxf(m, s_logC[s0 * L + ll]);
+        float z = 0.f;
+        for (int ll = 0; ll < L; ++ll) z += expf(s_logC[s0 * L + ll] - m);
+        aux[ao.logc + s0] = m + logf(z);
+    }
+    for (int ll = tid; ll < L; ll += nt) {
+        float m = -INFINITY;
+        for (int s0 = 0; s0 < S; ++s0) m = fmaxf(m, s_logC[s0 * L + ll]);
+        float z = 0.f;
+        for (int s0 = 0; s0 < S; ++s0) z += expf(s_logC[s0 * L + ll] - m);
+        aux[ao.logq + ll] = m + logf(z);
+    }
+}
+
+// sum_q part[q * stride] for q < n, added in q order (bit-reproducible) with eight L2 loads in flight at a time
+template <typename T>
+__device__ __forceinline__ T ordered_sum_ldcg(const T *__restrict__ part, int n, size_t stride) {
+    T acc = (T)0;
+    for (int q0 = 0; q0 < n; q0 += 8) {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = q0 + u < n ? __ldcg(part + (size_t)(q0 + u) * stride) : (T)0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    return acc;
+}
+
+// --------------------------------------------------------------------------------------------------
+// Level 3 of the hidden recurrence and what hangs off it, one CTA per block b of P steps (fhmm_small_forward's split
+// path leaves X_b and A^1..A^P in global memory): H_{bP+j} = X_b . A^j, hidden = log H, the block's rows of the mixing
+// matrix G, and the block's share of the time average. The CTA that finishes last adds the shares in block order (fixed
+// order: bit-reproducible) and writes Hbar, log C, log c, log q. One SM did all of this before, bound by its own shared-
+// memory bandwidth (23 us at config 3); the blocks are independent.
+__global__ void __launch_bounds__(256)
+fhmm_forward_expand(int S, int L, int I, int restricted, int KP, int P, const float *__restrict__ small,
+                    const double *__restrict__ Apow, const double *__restrict__ Xblk, float *__restrict__ hidden,
+                    double *__restrict__ Hlin, float *__restrict__ G, float *__restrict__ aux,
+                    double *__restrict__ HbarPart, int *__restrict__ ticket, int staged) {
+    const SmallOffsets so(S, L);
+    const AuxOffsets ao(S, L);
+    extern __shared__ double smd[];
+    const int SL = S * L, SS = S * S, NB = (I + P - 1) / P;
+    // staged != 0: the launch reserved room for X_b and A^1..A^(P-1) (one coalesced sweep instead of 2 S dependent
+    // L2 round trips per output)
+    double *s_X = smd;                                                  // [SL]
+    double *s_pow = s_X + SL;                                           // [P-1][L][S][S]
+    float *s_H = reinterpret_cast<float *>(staged ? s_pow + (size_t)(P - 1) * L * SS : smd);  // [P][SL]
+    float *s_w = s_H + P * SL;   // [L]
+    float *s_logC = s_w + L;     // [SL] (last CTA)
+    __shared__ int s_last;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int b = blockIdx.x, t_lo = b * P, len = min(I, t_lo + P) - t_lo;
+    const double *X = Xblk + (size_t)b * SL;
+    const double *Apw = Apow;
+    for (int i = tid; i < L; i += nt) s_w[i] = expf(small[so.log_w + i]);
+    if (staged) {
+        for (int i = tid; i < SL; i += nt) s_X[i] = X[i];
+#pragma unroll 8
+        for (int i = tid; i < (len - 1) * L * SS; i += nt) s_pow[i] = Apow[i];
+        __syncthreads();
+        X = s_X;
+        Apw = s_pow;
+    }
+    for (int o = tid; o < len * SL; o += nt) {
+        const int j = o / SL, e = o - j * SL, sp = e / L, l = e - sp * L;
+        double h;
+        if (j == 0) {
+            h = X[e];
+        } else {
+            const double *Aj = Apw + (size_t)(j - 1) * L * SS + (size_t)l * SS + sp;
+            double a0 = 0.0, a1 = 0.0;
+            int k = 0;
+            for (; k + 1 < S; k += 2) {
+                a0 = fma(X[k * L + l], Aj[k * S], a0);
+                a1 = fma(X[(k + 1) * L + l], Aj[(k + 1) * S], a1);
+            }
+            if (k < S) a0 = fma(X[k * L + l], Aj[k * S], a0);
+            h = a0 + a1;
+        }
+        const size_t i = (size_t)(t_lo + j) * SL + e;
+        Hlin[i] = h;
+        s_H[o] = (float)h;
+        hidden[i] = h > 1e-30 ? logf((float)h) : (float)log(h);
+    }
+    __syncthreads();
+    for (int e = tid; e < SL; e += nt) {
+        double acc = 0.0;
+        for (int j = 0; j < len; ++j) acc += (double)s_H[j * SL + e];
+        HbarPart[(size_t)b * SL + e] = acc;
+    }
+    // the mixing matrix G[t][k] = w_l H_t[s,l] (summed over l when the emission is shared between lineages)
+    for (int o = tid; o < len * KP; o += nt) {
+        const int j = o / KP, k = o - j * KP;
+        float g = 0.f;
+        if (restricted) {
+            if (k < S)
+                for (int ll = 0; ll < L; ++ll) g += s_H[j * SL + k * L + ll] * s_w[ll];
+        } else if (k < SL) {
+            g = s_H[j * SL + k] * s_w[k % L];
+        }
+        G[(size_t)(t_lo + j) * KP + k] = g;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(ticket, 1) == NB - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int e = tid; e < SL; e += nt) {
+        const double acc = ordered_sum_ldcg(HbarPart + e, NB, (size_t)SL);
+        const float hb = (float)(acc / (double)I);
+        aux[ao.Hbar + e] = hb;
+        const float lc = logf(hb) + small[so.log_w + e % L];
+        aux[ao.logC + e] = lc;
+        s_logC[e] = lc;
+    }
+    __syncthreads();
+    // log c_s = log sum_l C[s,l], log q_l = log sum_s C[s,l]
     for (int s0 = tid; s0 < S; s0 += nt) {
         float m = -INFINITY;
         for (int ll = 0; ll < L; ++ll) m = fmaxf(m, s_logC[s0 * L + ll]);
@@ -1462,6 +1597,235 @@ fhmm_small_backward(int S, int L, int I, int P, int restricted, int K, const flo
 }
 
 // --------------------------------------------------------------------------------------------------
+// The same backward as two multi-CTA kernels, one CTA per block of P steps (default; the blocks are independent apart
+// from the short chain over block boundaries, and one SM is slower at this than 23):
+//   fhmm_bwd_blocks   R_t = c_t + A R_{t+1} inside block b out of shared memory (a warp per lineage), the block's share
+//                     of gw; the CTA that finishes last runs the chain Y_b = R_{(b+1)P} + A^P Y_{b+1} and adds the gw
+//                     shares in block order
+//   fhmm_bwd_expand   gH_t = R_t + A^{e_b - t} Y_b for the block, the block's share of gA = sum_t H_t (x) gH_{t+1};
+//                     the CTA that finishes last adds the gA shares in block order and applies the softmax Jacobians of
+//                     pi, w, A and writes the 8 reported scalars
+__global__ void __launch_bounds__(512)
+fhmm_bwd_blocks(int S, int L, int I, int P, int restricted, int K, const float *__restrict__ small,
+                const float *__restrict__ aux, const float *__restrict__ gG, const double *__restrict__ scal,
+                const double *__restrict__ Hlin, const double *__restrict__ Apow, float *__restrict__ R,
+                float *__restrict__ gwPart, float *__restrict__ Yblk, float *__restrict__ gw_out,
+                int *__restrict__ ticket) {
+    const SmallOffsets so(S, L);
+    const AuxOffsets ao(S, L);
+    const ScalarOffsets sc(S, L, K);
+    extern __shared__ float sm[];
+    const int SL = S * L, SS = S * S, SP = S | 1, NB = (I + P - 1) / P;
+    float *s_A = sm;                          // [L][S][SP]: A
+    float *s_AP = s_A + L * S * SP;           // [L][S][SP]: A^P
+    float *s_AQ = s_AP + L * S * SP;          // [L][S][SP]: A^(length of the last block)
+    float *s_gg = s_AQ + L * S * SP;          // [P][K]
+    float *s_h = s_gg + P * K;                // [P][SL]
+    float *s_r0 = s_h + P * SL;               // [NB][SL] (last CTA): R at the first step of every block
+    __shared__ int s_last;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x, t_lo = b * P, t_hi = min(I, t_lo + P), len = t_hi - t_lo;
+    const int last_len = I - (NB - 1) * P;
+    for (int i = tid; i < L * SS; i += nt) {
+        const int o = (i / S) * SP + i % S;
+        s_A[o] = (float)Apow[i];
+        s_AP[o] = (float)Apow[(size_t)(P - 1) * L * SS + i];
+        s_AQ[o] = (float)Apow[(size_t)(last_len - 1) * L * SS + i];
+    }
+#pragma unroll 4
+    for (int i = tid; i < len * K; i += nt) s_gg[i] = gG[(size_t)t_lo * K + i];
+#pragma unroll 4
+    for (int i = tid; i < len * SL; i += nt) s_h[i] = (float)Hlin[(size_t)t_lo * SL + i];
+    // (the per-lane constants are fetched in the same round trip as the staging loads)
+    const bool on = lane < S && warp < L;
+    const int sl = on ? lane * L + warp : 0;
+    const float base = on ? (float)scal[sc.glogC + sl] / ((float)I * fmaxf(aux[ao.Hbar + sl], FLT_MIN)) : 0.f;
+    const float wl = expf(small[so.log_w + (warp < L ? warp : 0)]);
+    __syncthreads();
+    if (warp < L) {
+        const int l = warp;
+        const float *Arow = s_A + (l * S + (on ? lane : 0)) * SP;
+        const int kidx = restricted ? (on ? lane : 0) : sl;
+        float r_next = 0.f, gw_part = 0.f;  // gw_l = sum_{t,s} gG_t[s,l] H_t[s,l]
+        for (int j = len - 1; j >= 0; --j) {
+            const float gg = on ? s_gg[j * K + kidx] : 0.f;
+            if (on) gw_part = fmaf(gg, s_h[j * SL + sl], gw_part);
+            float a0 = on ? fmaf(wl, gg, base) : 0.f, a1 = 0.f;
+            if (j + 1 < len) {
+                int sp = 0;
+                for (; sp + 1 < S; sp += 2) {
+                    const float n0 = __shfl_sync(0xffffffffu, r_next, sp), n1 = __shfl_sync(0xffffffffu, r_next, sp + 1);
+                    a0 = fmaf(Arow[sp], n0, a0);
+                    a1 = fmaf(Arow[sp + 1], n1, a1);
+                }
+                if (sp < S) a0 = fmaf(Arow[sp], __shfl_sync(0xffffffffu, r_next, sp), a0);
+            }
+            r_next = on ? a0 + a1 : 0.f;
+            if (on) R[(size_t)(t_lo + j) * SL + sl] = r_next;
+        }
+        gw_part = warp_sum(gw_part);
+        if (lane == 0) gwPart[b * L + l] = gw_part;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(ticket, 1) == NB - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll 4
+    for (int i = tid; i < NB * SL; i += nt) s_r0[i] = __ldcg(R + (size_t)(i / SL) * P * SL + i % SL);
+    for (int l = tid; l < L; l += nt) {
+        gw_out[l] = ordered_sum_ldcg(gwPart + l, NB, (size_t)L);
+    }
+    __syncthreads();
+    if (warp < L) {  // Y_b = gH at the first step after block b (0 for the last block)
+        const int l = warp;
+        const bool on = lane < S;
+        const int sl = on ? lane * L + l : 0;
+        float y = 0.f;
+        for (int q = NB - 1; q >= 0; --q) {
+            if (on) Yblk[(size_t)q * SL + sl] = y;
+            if (q == 0) break;
+            // Y_{q-1} = gH_{qP} = R_{qP} + A^{length of block q} Y_q
+            const float *Arow = (q == NB - 1 ? s_AQ : s_AP) + (l * S + (on ? lane : 0)) * SP;
+            float a0 = on ? s_r0[q * SL + sl] : 0.f, a1 = 0.f;
+            int sp = 0;
+            for (; sp + 1 < S; sp += 2) {
+                const float n0 = __shfl_sync(0xffffffffu, y, sp), n1 = __shfl_sync(0xffffffffu, y, sp + 1);
+                a0 = fmaf(Arow[sp], n0, a0);
+                a1 = fmaf(Arow[sp + 1], n1, a1);
+            }
+            if (sp < S) a0 = fmaf(Arow[sp], __shfl_sync(0xffffffffu, y, sp), a0);
+            y = on ? a0 + a1 : 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fhmm_bwd_expand(int S, int L, int I, int P, int restricted, int K, const float *__restrict__ small,
+                const double *__restrict__ Hlin, const double *__restrict__ Apow, const float *__restrict__ aux,
+                const double *__restrict__ scal, const float *__restrict__ R, const float *__restrict__ Yblk,
+                const float *__restrict__ gw_in, float w_sparse, float w_excl, float w_orth, float w_tpm,
+                float *__restrict__ gAPart, float *__restrict__ gH0, float *__restrict__ g_pi, float *__restrict__ g_w,
+                float *__restrict__ g_A, float *__restrict__ terms, int *__restrict__ ticket, int staged) {
+    const SmallOffsets so(S, L);
+    const AuxOffsets ao(S, L);
+    const ScalarOffsets sc(S, L, K);
+    const float *log_pi = small + so.log_pi, *log_w = small + so.log_w, *log_Amix = small + so.log_Amix;
+    extern __shared__ double smd[];
+    const int SL = S * L, SS = S * S, SP = S | 1, LSS = L * SS, NB = (I + P - 1) / P;
+    double *s_scal = smd;                                                        // [sc.total] (last CTA)
+    float *s_H = reinterpret_cast<float *>(s_scal + ((sc.total + 1) & ~1));      // [P][SL]
+    float *s_g = s_H + P * SL;                                                   // [P + 1][SL]: gH_t, then gH at (b+1)P
+    float *s_gA = s_g + (P + 1) * SL;                                            // [L][S][S] (last CTA)
+    float *s_A = s_gA + LSS;                                                     // [L][S][SP] (last CTA): A
+    float *s_w = s_A + L * S * SP;                                               // [L]
+    float *s_amd = s_w + L;                                                      // [S]
+    float *s_pw = s_amd + S;                                                     // [P][L][S][S] when staged: A^(j+1)
+    __shared__ int s_last;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x, t_lo = b * P, len = min(I, t_lo + P) - t_lo;
+    for (int i = tid; i < SL; i += nt) s_g[len * SL + i] = Yblk[(size_t)b * SL + i];
+#pragma unroll 4
+    for (int i = tid; i < len * SL; i += nt) s_H[i] = (float)Hlin[(size_t)t_lo * SL + i];
+    if (staged) {
+#pragma unroll 8
+        for (int i = tid; i < len * LSS; i += nt) s_pw[i] = (float)Apow[i];
+    }
+    __syncthreads();
+    for (int o = tid; o < len * SL; o += nt) {
+        const int j = o / SL, e = o - j * SL, s0 = e / L, l = e - s0 * L;
+        const int pw = len - j;  // steps to the end of the block, >= 1
+        const size_t arow = (size_t)(pw - 1) * LSS + (size_t)l * SS + (size_t)s0 * S;
+        const float *Y = s_g + len * SL + l;
+        float a0 = R[(size_t)t_lo * SL + o], a1 = 0.f;
+        int sp = 0;
+        if (staged) {
+            const float *Arow = s_pw + arow;
+            for (; sp + 1 < S; sp += 2) {
+                a0 = fmaf(Arow[sp], Y[sp * L], a0);
+                a1 = fmaf(Arow[sp + 1], Y[(sp + 1) * L], a1);
+            }
+            if (sp < S) a0 = fmaf(Arow[sp], Y[sp * L], a0);
+        } else {
+            const double *Arow = Apow + arow;
+            for (; sp + 1 < S; sp += 2) {
+                a0 = fmaf((float)Arow[sp], Y[sp * L], a0);
+                a1 = fmaf((float)Arow[sp + 1], Y[(sp + 1) * L], a1);
+            }
+            if (sp < S) a0 = fmaf((float)Arow[sp], Y[sp * L], a0);
+        }
+        s_g[o] = a0 + a1;
+        if (t_lo + j == 0) gH0[e] = a0 + a1;
+    }
+    __syncthreads();
+    // the block's share of gA[l,s,s'] = sum_{t=0}^{I-2} H_t[s,l] gH_{t+1}[s',l]
+    {
+        const int jmax = min(len, I - 1 - t_lo);  // steps t of this block with t <= I - 2
+        for (int o = tid; o < LSS; o += nt) {
+            const int l = o / SS, s0 = (o / S) % S, sp = o % S;
+            const float *h = s_H + s0 * L + l, *g = s_g + SL + sp * L + l;
+            float a0 = 0.f, a1 = 0.f;
+            int j = 0;
+            for (; j + 1 < jmax; j += 2) {
+                a0 = fmaf(h[j * SL], g[j * SL], a0);
+                a1 = fmaf(h[(j + 1) * SL], g[(j + 1) * SL], a1);
+            }
+            if (j < jmax) a0 = fmaf(h[j * SL], g[j * SL], a0);
+            gAPart[(size_t)b * LSS + o] = a0 + a1;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(ticket, 1) == NB - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- last CTA: add the shares in block order, then the softmax Jacobians and the reported scalars
+    for (int i = tid; i < sc.total; i += nt) s_scal[i] = scal[i];
+    for (int o = tid; o < LSS; o += nt) {
+        s_gA[o] = ordered_sum_ldcg(gAPart + o, NB, (size_t)LSS);
+        s_A[(o / S) * SP + o % S] = (float)Apow[o];
+    }
+    for (int i = tid; i < L; i += nt) s_w[i] = expf(log_w[i]);
+    for (int i = tid; i < S; i += nt) s_amd[i] = expf(log_Amix[i * S + i]);
+    __syncthreads();
+    if (warp < L) {  // theta_pi: glogpi = pi * gH_0, softmax over s (per lineage)
+        const int l = warp;
+        const bool on = lane < S;
+        const float pi = on ? expf(log_pi[lane * L + l]) : 0.f;
+        const float pg = on ? pi * __ldcg(gH0 + lane * L + l) : 0.f;
+        const float dot = warp_sum(pg);
+        if (on) g_pi[lane * L + l] = pg - pi * dot;
+    }
+    for (int r = tid; r < L * S; r += nt) {  // theta_A: glogA = A*gA + sparsity part on the diagonal, softmax over s'
+        const int l = r / S, s0 = r % S;
+        const float *Ar = s_A + (size_t)r * SP;
+        const float diag = -w_sparse / (float)S * s_w[l] * Ar[s0] / s_amd[s0];
+        float sum = 0.f;
+        for (int sp = 0; sp < S; ++sp) sum += Ar[sp] * s_gA[(size_t)r * S + sp] + (sp == s0 ? diag : 0.f);
+        for (int sp = 0; sp < S; ++sp) {
+            const float gl = Ar[sp] * s_gA[(size_t)r * S + sp] + (sp == s0 ? diag : 0.f);
+            g_A[(size_t)r * S + sp] = gl - Ar[sp] * sum;
+        }
+    }
+    if (tid == 0) {  // theta_w: glogw_l = w_l*gw_l + sum_s glogC[s,l] + sparsity part
+        float glw[kMaxL], sum = 0.f;
+        for (int l = 0; l < L; ++l) {
+            float g = s_w[l] * gw_in[l];
+            for (int s0 = 0; s0 < S; ++s0) {
+                g += (float)s_scal[sc.glogC + s0 * L + l];
+                g += -w_sparse / (float)S * s_w[l] * s_A[(size_t)(l * S + s0) * SP + s0] / s_amd[s0];
+            }
+            glw[l] = g;
+            sum += g;
+        }
+        for (int l = 0; l < L; ++l) g_w[l] = glw[l] - s_w[l] * sum;
+        write_terms(S, L, K, s_scal, aux[ao.sparsity], w_sparse, w_excl, w_orth, w_tpm, terms);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // fhmm_bwd_local + fhmm_small_backward as ONE CTA of 1,024 threads that works out of shared memory. The two kernels
 // above walk R, H and gG in global memory inside loops whose iterations each wait for an L2 round trip (24 + 104 us at
 // config 3 with every SM but one idle); here A^1..A^P, R (-> gH), H, gG and the node-level scalars are staged once with
@@ -2137,6 +2501,8 @@ struct FhmmWs {
     int nsplitA, tchunkA;
     size_t R;
     size_t gwacc;  // [kMaxL] floats: dLoss/dw partial sums of fhmm_bwd_local
+    // split path of the small kernels (one CTA per block of P steps): per-block hand-over buffers
+    size_t Xblk, HbarPart, Yblk, gAPart, gwPart, gH0, tickets;
 };
 
 size_t up(size_t x) { return (x + 255) / 256 * 256; }
@@ -2245,6 +2611,19 @@ FhmmWs fhmm_layout(int S, int L, int Le, int N, int I) {
     w.Apow = take(sizeof(double) * (size_t)w.P * L * S * S);
     w.R = w.two_pass ? take(sizeof(float) * (size_t)I * N) : 0;
     w.gwacc = take(sizeof(float) * kMaxL);
+    {
+        size_t f1, b1;
+        const int P1 = choose_block(S, 1, I, &f1, &b1);  // the LSSM runs the same kernels with one lineage
+        const int Pmin = w.P < P1 ? w.P : P1;
+        const size_t NBmax = (size_t)(I + Pmin - 1) / Pmin;
+        w.Xblk = take(sizeof(double) * NBmax * S * L);
+        w.HbarPart = take(sizeof(double) * NBmax * S * L);
+        w.Yblk = take(sizeof(float) * NBmax * S * L);
+        w.gAPart = take(sizeof(float) * NBmax * L * S * S);
+        w.gwPart = take(sizeof(float) * NBmax * L);
+        w.gH0 = take(sizeof(float) * (size_t)S * L);
+        w.tickets = take(sizeof(int) * 4);
+    }
     w.total = off;
     return w;
 }
@@ -2368,12 +2747,46 @@ int32_t check_dims(int S, int L, int N, int I, int restricted) {
 
 // Backward of the hidden recurrence: the fused shared-memory kernel when its staging fits one CTA, else the two-kernel
 // path. CY2P_FHMM_FUSED_BWD=0 forces the latter (measurement).
+struct SplitBufs {  // FhmmWs::{Xblk, HbarPart, Yblk, gAPart, gwPart, gH0, tickets} resolved to pointers
+    double *Xblk, *HbarPart;
+    float *Yblk, *gAPart, *gwPart, *gH0;
+    int *tickets;
+};
+SplitBufs split_bufs(const FhmmWs &w, char *ws) {
+    return SplitBufs{(double *)(ws + w.Xblk), (double *)(ws + w.HbarPart), (float *)(ws + w.Yblk),
+                     (float *)(ws + w.gAPart), (float *)(ws + w.gwPart), (float *)(ws + w.gH0), (int *)(ws + w.tickets)};
+}
+// The split path needs blocks (P > 1) and the tickets fhmm_small_forward zeroes in the same call.
+bool use_split(int P) { return P > 1 && env_flag("CY2P_FHMM_SPLIT_SMALL", 1) != 0; }
+
 int32_t launch_hidden_backward(int S, int L, int I, int P, int restricted, int K, const float *small,
                                const double *Hlin, const double *Apow, const float *aux, const float *gG,
                                const double *scal, float w_sparse, float w_excl, float w_orth, float w_tpm, float *gH,
                                float *g_pi, float *g_w, float *g_A, float *terms, float *gwacc, size_t smem_local,
-                               size_t smem_bwd, cudaStream_t st) {
+                               size_t smem_bwd, cudaStream_t st, const SplitBufs &sb) {
     const ScalarOffsets sc(S, L, K);
+    if (use_split(P)) {
+        const int NB = (I + P - 1) / P, SL = S * L, SP = S | 1;
+        const size_t sm1 = sizeof(float) * ((size_t)3 * L * S * SP + (size_t)P * K + (size_t)P * SL + (size_t)NB * SL);
+        size_t sm2 = sizeof(double) * (size_t)((sc.total + 1) & ~1) +
+                     sizeof(float) * ((size_t)P * SL + (size_t)(P + 1) * SL + (size_t)L * S * S + (size_t)L * S * SP + L + S);
+        const size_t pw_bytes = sizeof(float) * (size_t)P * L * S * S;  // A^1..A^P as float, staged when they fit
+        const int staged = sm2 + pw_bytes <= 160 * 1024 ? 1 : 0;
+        if (staged) sm2 += pw_bytes;
+        if (sm1 <= 200 * 1024 && sm2 <= 200 * 1024) {
+            CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+            count_launch();
+            fhmm_bwd_blocks<<<NB, L * 32, sm1, st>>>(S, L, I, P, restricted, K, small, aux, gG, scal, Hlin, Apow, gH,
+                                                     sb.gwPart, sb.Yblk, gwacc, sb.tickets + 1);
+            CY2P_CUDA(cudaFuncSetAttribute(fhmm_bwd_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+            count_launch();
+            fhmm_bwd_expand<<<NB, 256, sm2, st>>>(S, L, I, P, restricted, K, small, Hlin, Apow, aux, scal, gH, sb.Yblk,
+                                                  gwacc, w_sparse, w_excl, w_orth, w_tpm, sb.gAPart, sb.gH0, g_pi, g_w,
+                                                  g_A, terms, sb.tickets + 2, staged);
+            CY2P_CUDA(cudaGetLastError());
+            return CY2P_OK;
+        }
+    }
     const int nt = 1024;
     const size_t fused = sizeof(double) * (size_t)((sc.total + 1) & ~1) + sizeof(float) * fused_bwd_floats(S, L, I, P, K, nt);
     if (fused <= 227 * 1024 && env_flag("CY2P_FHMM_FUSED_BWD", 1)) {
@@ -2416,15 +2829,30 @@ int32_t run_small_forward(int S, int L, int I, int restricted, const float *thet
         set_error("model too large for the one-CTA recurrence kernels (S=%d, L=%d, I=%d)", S, L, I);
         return CY2P_ERR_INVALID_ARG;
     }
+    const SplitBufs sb = split_bufs(w, ws);
+    size_t smx = sizeof(float) * ((size_t)w.P * S * L + L + (size_t)S * L);
+    const size_t stage_bytes = sizeof(double) * ((size_t)S * L + (size_t)(w.P - 1) * L * S * S);
+    const int staged = smx + stage_bytes <= 160 * 1024 ? 1 : 0;
+    if (staged) smx += stage_bytes;
+    const bool split = use_split(w.P) && smx <= 200 * 1024;
     const size_t hf_bytes = sizeof(float) * (size_t)I * S * L;  // float copy of H in shared memory when it fits
-    const int hf = (w.smem_fwd + hf_bytes <= 227 * 1024 && env_flag("CY2P_FHMM_HF_SMEM", 1)) ? 1 : 0;
+    const int hf = (!split && w.smem_fwd + hf_bytes <= 227 * 1024 && env_flag("CY2P_FHMM_HF_SMEM", 1)) ? 1 : 0;
     const size_t smem = w.smem_fwd + (hf ? hf_bytes : 0);
     CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     count_launch();
     fhmm_small_forward<<<1, 1024, smem, st>>>(S, L, I, restricted, w.KP, w.P, theta_pi, theta_w, theta_A,
                                               (float *)(ws + w.small), (float *)(ws + w.hidden), (float *)(ws + w.G),
                                               (float *)(ws + w.aux), (double *)(ws + w.Hlin), (double *)(ws + w.Apow),
-                                              hf);
+                                              hf, split ? sb.Xblk : nullptr, sb.tickets);
+    if (split) {
+        const int NB = (I + w.P - 1) / w.P;
+        CY2P_CUDA(cudaFuncSetAttribute(fhmm_forward_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smx));
+        count_launch();
+        fhmm_forward_expand<<<NB, 256, smx, st>>>(S, L, I, restricted, w.KP, w.P, (const float *)(ws + w.small),
+                                                  (const double *)(ws + w.Apow), sb.Xblk, (float *)(ws + w.hidden),
+                                                  (double *)(ws + w.Hlin), (float *)(ws + w.G), (float *)(ws + w.aux),
+                                                  sb.HbarPart, sb.tickets, staged);
+    }
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
 }
@@ -2488,15 +2916,30 @@ int32_t lssm_run_forward(int S, int L, int Le, int N, int I, int restricted, con
         return CY2P_ERR_INVALID_ARG;
     }
     CY2P_CUDA(cudaMemsetAsync(ws + w.zero, 0, sizeof(float) * 4, st));  // theta_w of the single lineage
+    const SplitBufs sb = split_bufs(w.f, ws);
+    size_t smx = sizeof(float) * ((size_t)w.P1 * S + 1 + (size_t)S);
+    const size_t stage_bytes = sizeof(double) * ((size_t)S + (size_t)(w.P1 - 1) * S * S);
+    const int staged = smx + stage_bytes <= 160 * 1024 ? 1 : 0;
+    if (staged) smx += stage_bytes;
+    const bool split = use_split(w.P1) && smx <= 200 * 1024;
     const size_t hf_bytes = sizeof(float) * (size_t)I * S;
-    const int hf = (w.smem_fwd1 + hf_bytes <= 227 * 1024 && env_flag("CY2P_FHMM_HF_SMEM", 1)) ? 1 : 0;
+    const int hf = (!split && w.smem_fwd1 + hf_bytes <= 227 * 1024 && env_flag("CY2P_FHMM_HF_SMEM", 1)) ? 1 : 0;
     const size_t smem1 = w.smem_fwd1 + (hf ? hf_bytes : 0);
     CY2P_CUDA(cudaFuncSetAttribute(fhmm_small_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     count_launch();
     fhmm_small_forward<<<1, 1024, smem1, st>>>(S, 1, I, 1, w.KP1, w.P1, theta_pi, (const float *)(ws + w.zero), theta_A,
                                                (float *)(ws + w.small1), (float *)(ws + w.f.hidden),
                                                (float *)(ws + w.G1), (float *)(ws + w.aux1), (double *)(ws + w.f.Hlin),
-                                               (double *)(ws + w.Apow1), hf);
+                                               (double *)(ws + w.Apow1), hf, split ? sb.Xblk : nullptr, sb.tickets);
+    if (split) {
+        const int NB1 = (I + w.P1 - 1) / w.P1;
+        CY2P_CUDA(cudaFuncSetAttribute(fhmm_forward_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smx));
+        count_launch();
+        fhmm_forward_expand<<<NB1, 256, smx, st>>>(S, 1, I, 1, w.KP1, w.P1, (const float *)(ws + w.small1),
+                                                   (const double *)(ws + w.Apow1), sb.Xblk, (float *)(ws + w.f.hidden),
+                                                   (double *)(ws + w.f.Hlin), (float *)(ws + w.G1),
+                                                   (float *)(ws + w.aux1), sb.HbarPart, sb.tickets, staged);
+    }
     count_launch();
     lssm_mix_forward<<<1, 512, 0, st>>>(S, L, I, restricted, w.f.KP, prenorm, theta_w, (const float *)(ws + w.small1),
                                         (const float *)(ws + w.aux1), (const double *)(ws + w.f.Hlin),
@@ -2557,7 +3000,8 @@ int32_t lssm_loss_core(cy2p_plan *plan, int S, int L, int Le, int N, int I, int 
     rc = launch_hidden_backward(S, 1, I, w.P1, 1, S, (const float *)(ws + w.small1), (const double *)(ws + w.f.Hlin),
                                 (const double *)(ws + w.Apow1), (const float *)(ws + w.aux1),
                                 (const float *)(ws + w.gG1), scal1, w_sparse, 0.f, 0.f, 0.f, (float *)(ws + w.f.gH),
-                                d_gpi, tmp, d_gA, tmp + 4, (float *)(ws + w.f.gwacc), w.smem_local1, w.smem_bwd1, st);
+                                d_gpi, tmp, d_gA, tmp + 4, (float *)(ws + w.f.gwacc), w.smem_local1, w.smem_bwd1, st,
+                                split_bufs(w.f, ws));
     if (rc) return rc;
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
@@ -2777,7 +3221,7 @@ int32_t cy2p_fhmm_loss_grad(cy2p_plan *plan, int32_t S, int32_t L, int32_t N, in
                                 (const double *)(ws + w.Hlin), (const double *)(ws + w.Apow),
                                 (const float *)(ws + w.aux), (const float *)(ws + w.gG), scal, w_sparse, w_excl, w_orth,
                                 w_tpm, (float *)(ws + w.gH), d_gpi, d_gw, d_gA, d_terms, (float *)(ws + w.gwacc),
-                                w.smem_local, w.smem_bwd, st);
+                                w.smem_local, w.smem_bwd, st, split_bufs(w, ws));
     if (rc) return rc;
     CY2P_CUDA(cudaGetLastError());
     return CY2P_OK;
