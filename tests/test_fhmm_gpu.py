@@ -158,6 +158,45 @@ def test_training_reduces_loss_at_moderate_size():
     assert m.loss_values[-1] < 0.7 * m.loss_values[0]
 
 
+@pytest.mark.parametrize("kind,S,L,I", [("fhmm", 10, 4, 130), ("fhmm", 7, 3, 45), ("lssm", 6, 3, 130), ("nssm", 5, 2, 61)])
+def test_recurrence_kernel_variants_agree(monkeypatch, kind, S, L, I):
+    """The hidden-state recurrences have three implementations: one CTA per block of P steps (default), one fused
+    shared-memory CTA (CY2P_FHMM_SPLIT_SMALL=0) and the round-1 pair of latency-bound kernels (also
+    CY2P_FHMM_FUSED_BWD=0, CY2P_FHMM_HF_SMEM=0). Same algebra, different summation order: loss terms, forward outputs and
+    the four gradients must agree to float32 rounding. I = 45 / 61 leave a short last block."""
+    from cy2path_b200 import _lib, models
+    from cy2path_b200.sampling import get_plan
+    from cy2path_b200.synth import knn_velocity_tpm
+
+    N = 2500
+    g = knn_velocity_tpm(N, k=12, seed=21)
+    plan = get_plan(g["T"])
+    x0 = torch.tensor((g["root_cells"] / g["root_cells"].sum()).astype(np.float32)).cuda()
+    D = _lib.propagate(plan, x0, I, history_stride=1, want_final=False)["history"].contiguous()
+    torch.manual_seed(5)
+    cls = {"fhmm": models.FHMM, "lssm": models.LSSM, "nssm": models.NSSM}[kind]
+    m = cls(S, L, N, I, restricted=True, use_gpu=True)
+    params = [p.data for p in m.parameters()]
+    wts = (1.0, 0.1, 0.1, 0.05)
+
+    def run(split, fused, hf):
+        monkeypatch.setenv("CY2P_FHMM_SPLIT_SMALL", str(split))
+        monkeypatch.setenv("CY2P_FHMM_FUSED_BWD", str(fused))
+        monkeypatch.setenv("CY2P_FHMM_HF_SMEM", str(hf))
+        terms, grads, _ = _lib.fhmm_loss_grad(plan, *params, D, True, wts, model=kind)
+        fwd = _lib.fhmm_forward(*params, I, True, want_pred=True, model=kind)
+        return (terms.cpu().numpy().copy(), [x.cpu().numpy().copy() for x in grads],
+                fwd["pred"].cpu().numpy().copy(), fwd["hidden"].cpu().numpy().copy())
+
+    base = run(0, 0, 0)
+    for variant in (run(1, 1, 1), run(0, 1, 1), run(0, 0, 1)):
+        assert np.abs(variant[0] - base[0]).max() <= 2e-6 * max(1.0, np.abs(base[0]).max())
+        for a, b in zip(variant[1], base[1]):
+            assert np.abs(a - b).max() <= 1e-7 + 2e-5 * np.abs(b).max()
+        assert np.abs(variant[2] - base[2]).max() <= 1e-5
+        assert np.abs(variant[3] - base[3]).max() <= 1e-5
+
+
 @pytest.mark.parametrize("name", GOLDEN)
 def test_decoders_match_reference_golden(golden, name):
     """filtering / smoothing / viterbi on the reference's 3-epoch-trained parameters."""
