@@ -61,6 +61,12 @@ struct XArgs {
     const double *pi_rows;
     unsigned long long *eps_acc;  // [kXEpsCopies][ncols][2] fixed-point sums of this update
     const double *eps_scale;      // device scalar
+    // Plain-grid launches: the CTA of (row block rb, slab) parks its 2 x CPL x 32 fixed-point sums at
+    // eps_part[(rb * nslabs + slab) * 2 * CPL * 32] with coalesced stores and x_eps_reduce adds them afterwards. The
+    // 512 64-bit reductions a CTA used to issue itself kept its registers resident for another ~3 us (of ~64): 5% of
+    // the update (profiles/k1x_epsdbg_r02.jsonl). Null: reduce straight into eps_acc (persistent / multi variants).
+    unsigned long long *eps_part;
+    int32_t dbg;                  // CY2PX_EPS_DBG (measurement only): 1 no global flush, 2 no epilogue, 4 no prologue + epilogue, 8 no pi load
 };
 
 __device__ __forceinline__ double mk_double(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
@@ -166,7 +172,8 @@ __device__ __forceinline__ void x_round(double y, uint32_t &hi, uint32_t &tail, 
 
 template <int LOB, int CPL, int WARPS, int U, bool IN_F32, bool OUT_F32, bool EPS>
 __device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int32_t row1, int slab, int copy_sel,
-                                               unsigned long long (*s_acc)[CPL][32], unsigned *s_done) {
+                                               unsigned long long (*s_acc)[CPL][32], unsigned *s_done,
+                                               int64_t part_slot = -1) {
     using F = XFmt<LOB, CPL>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int col = (slab * 32 + lane) * CPL;
@@ -179,7 +186,7 @@ __device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int
     // 3.69 vs 2.70 ms per update, profiles/k1x_sweep5_noeps_r02.jsonl); a call without a stationary vector passes
     // eps_acc == null and only skips the epilogue
     const bool want_eps = EPS && a.eps_acc != nullptr;
-    if (want_eps) {
+    if (want_eps && !(a.dbg & 4)) {
         for (int t = threadIdx.x; t < 2 * CPL * 32; t += WARPS * 32) (&s_acc[0][0][0])[t] = 0ull;
         if (threadIdx.x == 0) *s_done = 0u;
         __syncthreads();
@@ -210,7 +217,7 @@ __device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int
             const int32_t rn = r + WARPS;
             int32_t pn = 0, endn = 0;
             if (rn < row1) pn = __ldg(a.indptr + rn), endn = __ldg(a.indptr + rn + 1);
-            const double pi = want_eps ? __ldg(a.pi_rows + r) : 0.0;
+            const double pi = (want_eps && !(a.dbg & 8)) ? __ldg(a.pi_rows + r) : 1.0;
             const int32_t orow = (OUT_F32 && a.out_orig) ? __ldg(a.dest_ids + r) : r;
             double acc[CPL];
 #pragma unroll
@@ -317,7 +324,7 @@ __device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int
             }
         }
     }
-    if (want_eps) {
+    if (want_eps && !(a.dbg & 6)) {
         const double sc = __ldg(a.eps_scale);
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
@@ -329,8 +336,17 @@ __device__ __forceinline__ void gather_block_x(const XArgs &a, int32_t row0, int
         unsigned ticket = 0;
         if (lane == 0) ticket = atomicAdd(s_done, 1u);
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        if (ticket == WARPS - 1) {  // every warp's partials are in: one integer atomic per (column, which) and CTA
+        if (ticket == WARPS - 1 && !(a.dbg & 1)) {  // every warp's partials are in: one integer atomic per (column, which) and CTA
             __threadfence_block();
+            if (part_slot >= 0 && a.eps_part != nullptr) {
+                uint4 *dst = reinterpret_cast<uint4 *>(a.eps_part + part_slot * (2 * CPL * 32));
+                const volatile unsigned long long *src = &s_acc[0][0][0];
+#pragma unroll
+                for (int t = lane; t < CPL * 32; t += 32) {
+                    const unsigned long long v0 = src[2 * t], v1 = src[2 * t + 1];
+                    dst[t] = make_uint4((uint32_t)v0, (uint32_t)(v0 >> 32), (uint32_t)v1, (uint32_t)(v1 >> 32));
+                }
+            } else
             for (int t = lane; t < 2 * CPL * 32; t += 32) {
                 const int which = t / (CPL * 32), k = (t / 32) % CPL, ln = t & 31;
                 const int gcol = (slab * 32 + ln) * CPL + k;
@@ -350,7 +366,35 @@ spmm_gather_x(int32_t row_begin, int32_t row_end, int32_t rows_per_cta, XArgs a)
     __shared__ unsigned s_done;
     const int32_t row0 = row_begin + blockIdx.x * rows_per_cta;
     gather_block_x<LOB, CPL, WARPS, U, IN_F32, OUT_F32, EPS>(a, row0, min(row0 + rows_per_cta, row_end), blockIdx.y,
-                                                             blockIdx.x % kXEpsCopies, s_acc, &s_done);
+                                                             blockIdx.x % kXEpsCopies, s_acc, &s_done,
+                                                             (int64_t)blockIdx.x * gridDim.y + blockIdx.y);
+}
+
+// Adds the parked per-CTA sums of one update into eps_acc: thread = one (slab, which, column-in-lane, lane) entry and
+// one of gridDim.y interleaved shares of the row blocks; integer adds, so the order does not matter.
+template <int CPL>
+__global__ void __launch_bounds__(256)
+x_eps_reduce(int32_t nrb, int32_t nslabs, int32_t ncols, const unsigned long long *__restrict__ part,
+             unsigned long long *__restrict__ eps_acc) {
+    constexpr int PER = 2 * CPL * 32;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nslabs * PER) return;
+    const int slab = o / PER, idx = o - slab * PER;
+    const int which = idx / (CPL * 32), k = (idx / 32) % CPL, ln = idx & 31;
+    const int gcol = (slab * 32 + ln) * CPL + k;
+    if (gcol >= ncols) return;
+    const int QS = gridDim.y;
+    const unsigned long long *p = part + (size_t)slab * PER + idx;
+    const size_t stride = (size_t)nslabs * PER;
+    unsigned long long acc = 0ull;
+    for (int rb = blockIdx.y; rb < nrb; rb += QS * 8) {
+        unsigned long long v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = rb + u * QS < nrb ? __ldcg(p + (size_t)(rb + u * QS) * stride) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    atomicAdd(&eps_acc[((int64_t)(blockIdx.y % kXEpsCopies) * ncols + gcol) * 2 + which], acc);
 }
 
 // Persistent variant: num_SMs x MINB resident CTAs draw (column slab, row group) items from one counter in launch
@@ -535,7 +579,7 @@ static XConfig x_config(int lo_bits) {
 
 constexpr int kXCounterSlots = 4096;  // per-launch work counters of the persistent variant, zeroed per block of launches
 struct XWs {
-    size_t eps_acc, scal, part, bufA, bufB, pi_rows, counters, total;
+    size_t eps_acc, scal, part, bufA, bufB, pi_rows, counters, eps_part, total;
     int32_t tile;      // columns per tile (multiple of the slab width)
     uint32_t pitch;    // bytes per row of a scratch tile
 };
@@ -571,6 +615,12 @@ static XWs x_ws_layout(const cy2p_plan *plan, int32_t B, int32_t iters, int want
     if (want_eps) off = x_align_up(off + sizeof(double) * (size_t)plan->n, 256);
     w.counters = off;
     off = x_align_up(off + sizeof(int32_t) * kXCounterSlots, 256);
+    w.eps_part = off;
+    if (want_eps) {  // one parked block of sums per CTA of the densest plain launch (row blocks of >= 32 rows)
+        const int rpc = c.rows_per_cta < 64 ? (c.rows_per_cta < 32 ? 32 : c.rows_per_cta) : 64;
+        const size_t nrb = ((size_t)plan->n + rpc - 1) / rpc;
+        off = x_align_up(off + sizeof(unsigned long long) * nrb * (size_t)(w.tile / slab_cols) * 2 * slab_cols, 256);
+    }
     w.total = off;
     return w;
 }
@@ -607,6 +657,13 @@ static void x_launch_t(const XArgs &a, int32_t n, int rows_per_cta, cudaStream_t
     const dim3 grid((unsigned)((n + rows_per_cta - 1) / rows_per_cta), (unsigned)nslabs);
     count_launch();
     spmm_gather_x<LOB, CPL, WARPS, MINB, U, IN_F32, OUT_F32, true><<<grid, WARPS * 32, 0, st>>>(0, n, rows_per_cta, a);
+    if (a.eps_acc != nullptr && a.eps_part != nullptr) {
+        const int outs = nslabs * 2 * CPL * 32;
+        const int qs = grid.x >= 256 ? 16 : (grid.x >= 16 ? 4 : 1);
+        count_launch();
+        x_eps_reduce<CPL><<<dim3((unsigned)((outs + 255) / 256), (unsigned)qs), 256, 0, st>>>((int32_t)grid.x, nslabs, a.ncols,
+                                                                                         a.eps_part, a.eps_acc);
+    }
 }
 
 // tile -> tile updates (the bulk of a run): the tuning knobs select the instantiation. Measured on B200 at config 2
@@ -735,7 +792,7 @@ int32_t cy2p_propagate_x(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t 
         const bool multi = multi_env && iters >= 4 && c.cpl == 4 && c.warps == 8 && iters - 2 <= kXCounterSlots;
         for (int32_t it = 0; it < iters; ++it) {
             const bool first = it == 0, last = it + 1 == iters;
-            XArgs a;
+            XArgs a = {};
             a.indptr = reord ? plan->d_r_indptr : plan->d_t_indptr;
             a.pairs = reord ? (first ? plan->d_r_pairsD_op : plan->d_r_pairsD_pp) : plan->d_t_pairsD;
             a.dest_ids = reord ? plan->d_order : nullptr;
@@ -755,6 +812,9 @@ int32_t cy2p_propagate_x(cy2p_plan *plan, const float *d_X0, int32_t B, int32_t 
             a.pi_rows = pi_rows;
             a.eps_acc = d_eps ? eps_acc + 2 * (size_t)it * (size_t)nc * kXEpsCopies : nullptr;
             a.eps_scale = scal;
+            a.dbg = x_env_int("CY2PX_EPS_DBG", 0);
+            a.eps_part = (d_eps && c.rows_per_cta >= 32 && x_env_int("CY2PX_EPS_PARK", 1))
+                             ? (unsigned long long *)(ws + w.eps_part) : nullptr;
             if (multi && it == 1) {  // updates 1 .. iters-2 in ONE cooperative launch
                 const int32_t n_upd = iters - 2;
                 CY2P_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * kXCounterSlots, st));

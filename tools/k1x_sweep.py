@@ -32,6 +32,8 @@ for _t in (128, 256, 512, 2048):
     CONFIGS["f48_multi_c4_t%d" % _t] = ("x", 16, {"CY2PX_MULTI": "1", "CY2PX_CPL": "4", "CY2PX_MINB": "2", "CY2P_TILE": str(_t)})
     CONFIGS["f48_plain_c4_t%d" % _t] = ("x", 16, {"CY2PX_CPL": "4", "CY2PX_MINB": "2", "CY2P_TILE": str(_t)})
 CONFIGS["f48_default"] = ("x", 16, {})
+for _d in (1, 2, 4, 8, 12):  # eps-epilogue cost breakdown (results are NOT valid in these modes)
+    CONFIGS["f48_epsdbg%d" % _d] = ("x", 16, {"CY2PX_EPS_DBG": str(_d)})
 CONFIGS["f40_default"] = ("x", 8, {})
 for _t in (128, 512, 1024):
     CONFIGS["f48_default_t%d" % _t] = ("x", 16, {"CY2P_TILE": str(_t)})
