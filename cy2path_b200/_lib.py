@@ -197,6 +197,46 @@ def to_host_many(tensors):
     return [None if o is None else o.numpy() for o in outs]
 
 
+# ------------------------------------------------------------------------------------------ guarded device buffers
+# compute-sanitizer is not available on the GPU pool this was developed on, so out-of-bounds WRITES are hunted with
+# canaries instead: with CY2P_GUARD=1 every device buffer the wrappers hand to the library (outputs and work spaces) is
+# carved out of a larger allocation with 64 KB of 0xA5 on either side, and check_guards() (after a synchronise) raises
+# if a single guard byte changed. tests/test_guards_gpu.py runs odd shapes of every entry point this way. Off by default:
+# one environment lookup per allocation.
+_GUARD_BYTES = 1 << 16
+_GUARDS = []
+
+
+def dev_empty(shape, dtype, dev, what="buffer"):
+    """torch.empty on the device, or — under CY2P_GUARD=1 — a view into a canary-fenced allocation."""
+    torch = _torch()
+    shape = tuple(int(v) for v in shape)
+    if os.environ.get("CY2P_GUARD", "0") in ("", "0"):
+        return torch.empty(shape, dtype=dtype, device=dev)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * torch.empty((), dtype=dtype).element_size()
+    pad = (-nbytes) % 256
+    flat = torch.full((2 * _GUARD_BYTES + nbytes + pad,), 0xA5, dtype=torch.uint8, device=dev)
+    _GUARDS.append((what, flat[:_GUARD_BYTES], flat[_GUARD_BYTES + nbytes:], flat))
+    return flat[_GUARD_BYTES:_GUARD_BYTES + nbytes].view(dtype).view(shape)
+
+
+def check_guards():
+    """Synchronise and verify every canary handed out since the last call; raises RuntimeError on a changed byte."""
+    torch = _torch()
+    bad = []
+    for what, lo, hi, _keep in _GUARDS:
+        torch.cuda.synchronize(lo.device)
+        if not bool((lo == 0xA5).all()):
+            bad.append("%s: bytes BEFORE the buffer were written" % what)
+        if not bool((hi == 0xA5).all()):
+            bad.append("%s: bytes AFTER the buffer were written" % what)
+    n = len(_GUARDS)
+    _GUARDS.clear()
+    if bad:
+        raise RuntimeError("out-of-bounds device writes: " + "; ".join(bad))
+    return n
+
+
 class Plan:
     """Device-resident T and T^T for one transition matrix on one device (cy2p_plan)."""
 
@@ -268,14 +308,14 @@ def propagate(plan, X0, iters, stationary=None, want_final=True, history_stride=
         if stationary is not None:
             st = torch.as_tensor(np.asarray(stationary, dtype=np.float64) if not torch.is_tensor(stationary)
                                  else stationary, dtype=torch.float64, device=dev).contiguous()
-        final = torch.empty_like(X0) if want_final else None
+        final = dev_empty(X0.shape, X0.dtype, dev, "propagate final") if want_final else None
         hist = None
         if history_stride:
             slots = (iters + history_stride - 1) // history_stride
-            hist = torch.empty((max(slots, 1), plan.n, B), dtype=X0.dtype, device=dev)
-        eps = torch.empty((iters, B), dtype=torch.float64, device=dev) if want_eps else None
+            hist = dev_empty((max(slots, 1), plan.n, B), X0.dtype, dev, "propagate history")
+        eps = dev_empty((iters, B), torch.float64, dev, "propagate eps") if want_eps else None
         ws_bytes = ws_fn(plan.handle, B, iters)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = dev_empty((ws_bytes,), torch.uint8, dev, "propagate work space")
         check(fn(plan.handle, ptr(X0), B, iters, ptr(st), ptr(final), ptr(hist), max(history_stride, 1), ptr(eps),
                  ptr(ws), ws_bytes, stream_ptr(dev)))
     if squeeze:
@@ -302,10 +342,10 @@ def propagate_x(plan, X0, iters, stationary=None, tail_bits=16, want_eps=False, 
             st = torch.as_tensor(np.asarray(stationary, dtype=np.float64) if not torch.is_tensor(stationary)
                                  else stationary, dtype=torch.float64, device=dev).contiguous()
         want_eps = bool(want_eps and st is not None)
-        final = torch.empty((plan.n, B), dtype=torch.float64 if f64_out else torch.float32, device=dev)
-        eps = torch.empty((iters, B), dtype=torch.float64, device=dev) if want_eps else None
+        final = dev_empty((plan.n, B), torch.float64 if f64_out else torch.float32, dev, "propagate_x final")
+        eps = dev_empty((iters, B), torch.float64, dev, "propagate_x eps") if want_eps else None
         ws_bytes = lib.cy2p_propagate_x_ws_bytes(plan.handle, B, iters, int(want_eps), tail_bits)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = dev_empty((ws_bytes,), torch.uint8, dev, "propagate_x work space")
         check(lib.cy2p_propagate_x(plan.handle, ptr(X0), B, iters, ptr(st), None if f64_out else ptr(final),
                                    ptr(final) if f64_out else None, ptr(eps), tail_bits, ptr(ws), ws_bytes,
                                    stream_ptr(dev)))
@@ -330,7 +370,7 @@ def _fhmm_ws(S, L, N, I, dev, model="fhmm"):
     if nbytes == 0:
         raise ValueError("unsupported model size (supported: S <= 32, L <= 16, S*(1 if restricted else L) <= 64; "
                          "NSSM: S*L <= 64)")
-    return torch.empty(nbytes, dtype=torch.uint8, device=dev), nbytes
+    return dev_empty((nbytes,), torch.uint8, dev, "%s work space" % model), nbytes
 
 
 def fhmm_forward(theta_pi, theta_w, theta_E, theta_A, num_iters, restricted, want_pred=True, want_joint=False,
@@ -348,7 +388,7 @@ def fhmm_forward(theta_pi, theta_w, theta_E, theta_A, num_iters, restricted, wan
         N = theta_E.shape[1]
         with torch.cuda.device(dev):
             ws, nbytes = _fhmm_ws(S, L, N, I, dev, model)
-            f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)  # noqa: E731
+            f = lambda *shape: dev_empty(shape, torch.float32, dev, "model output")  # noqa: E731
             pred = f(I, N) if want_pred else None
             hidden, joint = f(I, S), (f(I, S, L, N) if want_joint else None)
             logE, logcw, small = f(S, N), f(*tw.shape), f(lib.cy2p_lssm_small_floats(S, L))
@@ -361,11 +401,11 @@ def fhmm_forward(theta_pi, theta_w, theta_E, theta_A, num_iters, restricted, wan
     Le, N = theta_E.shape[1], theta_E.shape[2]
     with torch.cuda.device(dev):
         ws, nbytes = _fhmm_ws(S, L, N, I, dev, model)
-        pred = torch.empty((I, N), dtype=torch.float32, device=dev) if want_pred else None
-        hidden = torch.empty((I, S, L) if model == "fhmm" else (I, S), dtype=torch.float32, device=dev)
-        joint = torch.empty((I, S, L, N), dtype=torch.float32, device=dev) if want_joint else None
-        logE = torch.empty((S, Le, N), dtype=torch.float32, device=dev)
-        small = torch.empty(getattr(lib, "cy2p_%s_small_floats" % model)(S, L), dtype=torch.float32, device=dev)
+        pred = dev_empty((I, N), torch.float32, dev, "forward pred") if want_pred else None
+        hidden = dev_empty((I, S, L) if model == "fhmm" else (I, S), torch.float32, dev, "forward hidden")
+        joint = dev_empty((I, S, L, N), torch.float32, dev, "forward joint") if want_joint else None
+        logE = dev_empty((S, Le, N), torch.float32, dev, "forward logE")
+        small = dev_empty((getattr(lib, "cy2p_%s_small_floats" % model)(S, L),), torch.float32, dev, "forward small")
         fwd = getattr(lib, "cy2p_%s_forward" % model)
         check(fwd(S, L, N, I, int(bool(restricted)), ptr(tp), ptr(tw), ptr(tE), ptr(tA), ptr(pred),
                   ptr(hidden), ptr(joint), ptr(logE), ptr(small), ptr(ws), nbytes, stream_ptr(dev)))
@@ -400,8 +440,8 @@ def fhmm_loss_grad(plan, theta_pi, theta_w, theta_E, theta_A, D, restricted, wei
     with torch.cuda.device(dev):
         if out is None:
             ws, nbytes = _fhmm_ws(S, L, N, I, dev, model)
-            out = {"ws": ws, "nbytes": nbytes, "terms": torch.empty(8, dtype=torch.float32, device=dev),
-                   "g": tuple(torch.empty_like(t) for t in (tp, tw, tE, tA))}
+            out = {"ws": ws, "nbytes": nbytes, "terms": dev_empty((8,), torch.float32, dev, "loss terms"),
+                   "g": tuple(dev_empty(t.shape, t.dtype, dev, "gradient %d" % i) for i, t in enumerate((tp, tw, tE, tA)))}
         hw = (ctypes.c_float * 4)(*[float(x) for x in weights])
         g = out["g"]
         tdst = out["terms"] if terms is None else terms  # 8 contiguous float32 (e.g. a row of the epoch history)
@@ -425,7 +465,7 @@ def fhmm_decode(theta_pi, theta_w, theta_E, theta_A, D, restricted, model="fhmm"
     D = D.to(dev, dtype=torch.float32).contiguous()
     with torch.cuda.device(dev):
         ws, nbytes = _fhmm_ws(S, L, N, I, dev, model)
-        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)  # noqa: E731
+        f = lambda *shape: dev_empty(shape, torch.float32, dev, "model output")  # noqa: E731
         out = {"log_alpha": f(I, S, L), "log_probs": f(I, L), "log_beta": f(I, S, L), "log_gamma": f(I, S, L),
                "log_delta": f(I, S, L), "psi": f(I, S, L), "log_max": f(I, L), "best_path": f(L, I)}
         fn = getattr(lib, "cy2p_%s_decode" % model)
@@ -454,11 +494,11 @@ def trajectory_distance_matrix(series, kind="dtw"):
     with torch.cuda.device(dev):
         s = torch.zeros((C, ln, dpad), dtype=torch.float64, device=dev)
         s[:, :, :d] = series.to(torch.float64)
-        out = torch.empty((C, C), dtype=torch.float64, device=dev)
+        out = dev_empty((C, C), torch.float64, dev, "distance matrix")
         if C == 0 or ln == 0:
             return out.zero_()
         nbytes = lib.cy2p_traj_ws_bytes(C, ln)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = dev_empty((nbytes,), torch.uint8, dev, "trajectory work space")
         fn = lib.cy2p_dtw_matrix if kind == "dtw" else lib.cy2p_hausdorff_matrix
         check(fn(ptr(s), C, ln, dpad, ptr(out), ptr(ws), nbytes, stream_ptr(dev)))
     return out

@@ -26,8 +26,8 @@ def _tables_device(plan):
     if getattr(plan, "_tables", None) is None:
         W = max(plan.W, 1)
         with torch.cuda.device(plan.device):
-            idx = torch.empty((plan.n, W), dtype=torch.int32, device=plan.device)
-            cum = torch.empty((plan.n, W), dtype=torch.float32, device=plan.device)
+            idx = _lib.dev_empty((plan.n, W), torch.int32, plan.device, "CDF idx")
+            cum = _lib.dev_empty((plan.n, W), torch.float32, plan.device, "CDF cum")
             _lib.check(_lib.load().cy2p_cdf_build(plan.handle, _lib.ptr(idx), _lib.ptr(cum), W,
                                                   _lib.stream_ptr(plan.device)))
         plan._tables = (idx, cum)
@@ -61,16 +61,16 @@ def _walk(plan, idx_d, cum_d, init_states, uniforms, want_history_steps=None, wa
             raise ValueError("one init state per chain required")
         if C and (int(init_d.min()) < 0 or int(init_d.max()) >= plan.n):
             raise IndexError("init_state out of range")
-        states = torch.empty((C, steps + 1), dtype=torch.int32, device=dev)
-        probs = torch.empty((C, steps), dtype=torch.float32, device=dev)
+        states = _lib.dev_empty((C, steps + 1), torch.int32, dev, "chain states")
+        probs = _lib.dev_empty((C, steps), torch.float32, dev, "chain probs")
         err = torch.zeros(4, dtype=torch.int32, device=dev)
         _lib.check(lib.cy2p_sample_chains(plan.handle, _lib.ptr(idx_d), _lib.ptr(cum_d), int(idx_d.shape[1]),
                                           _lib.ptr(init_d), _lib.ptr(u_d), C, steps, _lib.ptr(states),
                                           _lib.ptr(probs), _lib.ptr(err), _lib.stream_ptr(dev)))
         hist = counts = None
         if want_history_steps:
-            counts = torch.empty((want_history_steps, plan.n), dtype=torch.int32, device=dev)
-            hist = torch.empty((want_history_steps, plan.n), dtype=torch.float32, device=dev)
+            counts = _lib.dev_empty((want_history_steps, plan.n), torch.int32, dev, "visit counts")
+            hist = _lib.dev_empty((want_history_steps, plan.n), torch.float32, dev, "visit histogram")
             _lib.check(lib.cy2p_chain_history(_lib.ptr(states), C, steps + 1, want_history_steps, plan.n,
                                               _lib.ptr(counts), _lib.ptr(hist), _lib.stream_ptr(dev)))
     if want_counts:
