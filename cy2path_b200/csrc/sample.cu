@@ -115,6 +115,89 @@ sample_chains_kernel(int64_t C, int32_t steps, int32_t W, const int32_t *__restr
     }
 }
 
+// Canonical rows no longer than LANES * NCH: the whole CDF / index row of the current state (NCH loads of each per
+// lane) and the row pointer are requested at once, so a step costs two dependent L2 round trips (row, then T[prev,next])
+// instead of one per chunk plus two; with 8 lanes per chain a wave of resident threads also carries twice the chains of
+// the 16-lane chunked search. Measured at config 2 (100,000 chains x 2,000 steps, W = 30): see profiles/README_r02.md.
+template <int LANES, int NCH>
+__global__ void __launch_bounds__(256)
+sample_chains_prefetch(int64_t C, int32_t steps, int32_t W, const int32_t *__restrict__ idx,
+                       const float *__restrict__ cum, const int32_t *__restrict__ indptr,
+                       const float *__restrict__ data, const int32_t *__restrict__ init_state,
+                       const double *__restrict__ uniforms, int32_t *__restrict__ states, float *__restrict__ probs,
+                       int32_t *err) {
+    constexpr int GROUPS = 32 / LANES;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LANES;
+    const int gshift = (lane / LANES) * LANES;
+    const unsigned gmask = (unsigned)((LANES == 32 ? 0xffffffffull : ((1ull << LANES) - 1ull)) << gshift);
+    const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t chain = warp_global * GROUPS + lane / LANES;
+    const bool live = chain < C;
+    const int64_t ch = live ? chain : 0;
+    const double *u = uniforms + ch * (int64_t)steps;
+    int32_t *out_s = states + ch * ((int64_t)steps + 1);
+    float *out_p = probs + ch * (int64_t)steps;
+
+    int32_t state = init_state[ch];
+    if (live && gl == 0) out_s[0] = state;
+    bool dead = !live;
+
+    for (int32_t k0 = 0; k0 < steps; k0 += LANES) {
+        const int32_t m = min(LANES, steps - k0);
+        const double my_u = (live && gl < m) ? u[k0 + gl] : 0.0;
+        int32_t my_state = -1;
+        float my_prob = 0.f;
+        for (int32_t s = 0; s < m; ++s) {
+            const double r = __shfl_sync(0xffffffffu, my_u, gshift + s);
+            const int64_t base = (int64_t)state * W;
+            float cv[NCH];
+            int32_t iv[NCH];
+            const int32_t rp = dead ? 0 : __ldg(indptr + state);
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                const int32_t c = j * LANES + gl;
+                const bool in = !dead && c < W;
+                cv[j] = in ? __ldg(cum + base + c) : -1.f;  // uniforms are >= 0: a padding lane never hits
+                iv[j] = in ? __ldg(idx + base + c) : 0;
+            }
+            int32_t nxt = -1, col = 0;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                const unsigned hit = (__ballot_sync(0xffffffffu, cv[j] >= 0.f && r <= (double)cv[j]) & gmask) >> gshift;
+                const int first = hit ? __ffs(hit) - 1 : 0;
+                const int32_t got = __shfl_sync(0xffffffffu, iv[j], gshift + first);
+                if (nxt < 0 && hit) {
+                    nxt = got;
+                    col = j * LANES + first;
+                }
+            }
+            if (!dead && nxt < 0) {  // r above every CDF entry of the row: the reference raises IndexError here
+                if (gl == 0 && atomicCAS(&err[0], 0, 1) == 0) {
+                    err[1] = (int32_t)min(chain, (int64_t)INT32_MAX);
+                    err[2] = k0 + s + 1;
+                    err[3] = state;
+                }
+                dead = true;
+            }
+            float pr = 0.f;
+            if (!dead && gl == 0) pr = __ldg(data + rp + col);
+            pr = __shfl_sync(0xffffffffu, pr, gshift);
+            if (!dead) {
+                state = nxt;
+                if (gl == s) {
+                    my_state = nxt;
+                    my_prob = pr;
+                }
+            }
+        }
+        if (live && gl < m) {
+            out_s[k0 + 1 + gl] = my_state;  // -1 marks steps after an overshoot
+            out_p[k0 + gl] = my_prob;
+        }
+    }
+}
+
 __global__ void hist_count_kernel(int64_t C, int32_t ld_states, int32_t steps1, int32_t n,
                                   const int32_t *__restrict__ states, int32_t *__restrict__ counts) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,11 +251,28 @@ int32_t cy2p_sample_chains(const cy2p_plan *plan, const int32_t *d_idx, const fl
         int lanes = (ev && *ev) ? atoi(ev) : (W <= 8 ? 8 : 16);
 #define CY2P_SAMPLE(L_, C_) \
     launch_sampler<L_, C_>(C, steps, W, d_idx, d_cum, plan, d_init_state, d_uniforms, d_states, d_probs, d_err, st)
-        if (!canonical) CY2P_SAMPLE(32, false);
+#define CY2P_PREFETCH(L_, N_)                                                                                       \
+    do {                                                                                                            \
+        const int64_t per_cta = 8 * (32 / L_);                                                                      \
+        count_launch();                                                                                             \
+        sample_chains_prefetch<L_, N_><<<(unsigned)((C + per_cta - 1) / per_cta), 256, 0, st>>>(                    \
+            C, steps, W, d_idx, d_cum, plan->d_indptr, plan->d_data, d_init_state, d_uniforms, d_states, d_probs,   \
+            d_err);                                                                                                 \
+    } while (0)
+        const char *pv = getenv("CY2P_SAMPLER_PREFETCH");  // 0: the chunked search of round 1 (measurement)
+        const bool prefetch = canonical && !(ev && *ev) && !(pv && *pv && atoi(pv) == 0);
+        const char *lv = getenv("CY2P_SAMPLER_PF_LANES");  // tuning knob: lanes per chain of the prefetching kernel
+        const int pf_lanes = (lv && *lv) ? atoi(lv) : 8;
+        if (prefetch && W <= 32 && pf_lanes == 4) CY2P_PREFETCH(4, 8);
+        else if (prefetch && W <= 32 && pf_lanes == 16) CY2P_PREFETCH(16, 2);
+        else if (prefetch && W <= 32) CY2P_PREFETCH(8, 4);
+        else if (prefetch && W <= 64) CY2P_PREFETCH(8, 8);
+        else if (!canonical) CY2P_SAMPLE(32, false);
         else if (lanes <= 8) CY2P_SAMPLE(8, true);
         else if (lanes <= 16) CY2P_SAMPLE(16, true);
         else CY2P_SAMPLE(32, true);
 #undef CY2P_SAMPLE
+#undef CY2P_PREFETCH
         CY2P_CUDA(cudaGetLastError());
     }
     int32_t h[4] = {0, 0, 0, 0};
