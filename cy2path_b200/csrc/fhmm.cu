@@ -159,6 +159,9 @@ __global__ void __launch_bounds__(1024) fhmm_small_forward(int S, int L, int I, 
     float *s_amix = s_logw + L;           // [S][S]
     const int tid = threadIdx.x, nt = blockDim.x;
 
+    // last-CTA tickets of the multi-CTA recurrence kernels that follow in this call (forward expand, backward blocks,
+    // backward expand): zeroed here, by the first kernel of every forward / loss+grad call, whichever variants run later
+    if (tickets != nullptr && tid < 4) tickets[tid] = 0;
     // the three raw parameter blocks come in with one sweep of independent loads; the softmaxes then run out of shared
     // memory (their max / sum loops would otherwise wait for one L2 round trip per element)
     for (int i = tid; i < L * S * S; i += nt) s_logA[i] = theta_A[i];
@@ -274,7 +277,6 @@ __global__ void __launch_bounds__(1024) fhmm_small_forward(int S, int L, int I, 
     __syncthreads();
     if (Xblk != nullptr) {  // split path (P > 1): level 3 and everything after it run as fhmm_forward_expand, one CTA per block
         for (int i = tid; i < NB * SL; i += nt) Xblk[i] = s_X[i];
-        if (tid < 4) tickets[tid] = 0;  // last-CTA tickets of the three multi-CTA kernels that follow in this call
         return;
     }
     // level 3 + hidden = log H
