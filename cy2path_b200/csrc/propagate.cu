@@ -1246,10 +1246,21 @@ static int32_t propagate_impl(cy2p_plan *plan, const T *d_X0, int32_t B, int32_t
                     spmm_staged<T, SV, true><<<grid, kStagedWarps * 32, staged_smem, st>>>(sa);
                 else
                     spmm_staged<T, SV, false><<<grid, kStagedWarps * 32, staged_smem, st>>>(sa);
-            } else if (wide && (nc % VW == 0))
-                launch_gather<T, VW>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms,
-                                     pi_rows);
-            else
+            } else if (wide && (nc % VW == 0)) {
+                // CY2P_GATHER_VEC = 2 / 1 (experiment): a warp takes 256- / 128-byte row segments instead of 512-byte
+                // ones, so the SM's L1 holds 2x / 4x as many segments (LRU model of tools/reorder_lab.cpp: hit rate
+                // 22% -> 36% -> 50%) at the price of more (src,val) loads per operand byte
+                const int vec_env = env_int("CY2P_GATHER_VEC", 0);
+                if (sizeof(T) == 4 && vec_env == 2)
+                    launch_gather<T, 2>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms,
+                                        pi_rows);
+                else if (vec_env == 1)
+                    launch_gather<T, 1>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms,
+                                        pi_rows);
+                else
+                    launch_gather<T, VW>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt,
+                                         plan->num_sms, pi_rows);
+            } else
                 launch_gather<T, 1>(g, 0, n, src, ld_src, dst, ld_dst, nc, d_stationary, acc, st, cnt, plan->num_sms,
                                     pi_rows);
             src = dst;

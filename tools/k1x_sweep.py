@@ -18,6 +18,8 @@ def _x(tail, **env):
 
 CONFIGS = {
     "fp32": ("f32", 0, {}),
+    "fp32_vec2": ("f32", 0, {"CY2P_GATHER_VEC": "2"}),  # 256-byte row segments per warp
+    "fp32_vec1": ("f32", 0, {"CY2P_GATHER_VEC": "1"}),  # 128-byte row segments
     "fp64": ("f64", 0, {}),
 }
 for _tail, _nm in ((16, "f48"), (8, "f40")):
