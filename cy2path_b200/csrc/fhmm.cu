@@ -1109,7 +1109,21 @@ __global__ void csr_times_small(int n_rows, int B, const int32_t *__restrict__ i
     if (gid >= (int64_t)n_rows * B) return;
     const int r = (int)(gid / B), b = (int)(gid % B);
     float acc = 0.f;
-    for (int32_t p = indptr[r]; p < indptr[r + 1]; ++p) acc = fmaf(data[p], X[(size_t)indices[p] * B + b], acc);
+    const int32_t beg = indptr[r], end = indptr[r + 1];
+    for (int32_t p0 = beg; p0 < end; p0 += 8) {  // eight entries, then their eight gathers, in flight at a time
+        int32_t ix[8];
+        float dv[8], xv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool in = p0 + k < end;
+            ix[k] = in ? __ldg(indices + p0 + k) : 0;
+            dv[k] = in ? __ldg(data + p0 + k) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xv[k] = p0 + k < end ? __ldg(X + (size_t)ix[k] * B + b) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(dv[k], xv[k], acc);
+    }
     Y[gid] = acc;
 }
 

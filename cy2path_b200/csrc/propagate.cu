@@ -668,6 +668,33 @@ spmv_rows(int32_t row_begin, int32_t row_end, const int32_t *__restrict__ t_indp
     }
 }
 
+// 2 <= B <= 16 columns (the models' node-level products with T: B = S + L = 14 at config 3; the subspace iteration of
+// stationary.py: B = 10): a half-warp per destination row, lane = column, eight entries and eight row gathers in
+// flight. The general kernel gives such a row a whole warp with most lanes idle and one dependent (entry, gather) pair
+// at a time: 47 us for 50,000 rows x 30 entries x 14 columns (ncu: 27 cycles of latency per issued instruction).
+template <typename T>
+__global__ void __launch_bounds__(256)
+spmm_rows_narrow(int32_t row_begin, int32_t row_end, const int32_t *__restrict__ t_indptr, const Pair *__restrict__ pairs,
+                 const T *__restrict__ x, int32_t B, T *__restrict__ y) {
+    const int lane = threadIdx.x & 31, half = lane >> 4, col = lane & 15;
+    const int32_t r = row_begin + (int32_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + half);
+    const bool ok = r < row_end;
+    const int32_t beg = ok ? t_indptr[r] : 0, end = ok ? t_indptr[r + 1] : 0;
+    const bool live = col < B;
+    T acc = (T)0;
+    for (int32_t p0 = beg; p0 < end; p0 += 8) {
+        Pair e[8];
+        T xv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = p0 + k < end ? pairs[p0 + k] : Pair{0, 0.f};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xv[k] = (live && p0 + k < end) ? __ldg(x + (size_t)e[k].src * B + col) : (T)0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fma((T)e[k].val, xv[k], acc);
+    }
+    if (ok && live) y[(size_t)r * B + col] = acc;
+}
+
 // Persistent single-start update of a row range for the row-partitioned run (config 5, B == 1): ALL updates in one
 // cooperative launch. Per update: the rank's rows (8 lanes per row, as spmv_rows) are formed from its full-size
 // iterate and stored into the next-iterate buffers of the ranks that gather them (own HBM + NVLink peer stores, per-row
@@ -1296,6 +1323,11 @@ static int32_t propagate_rows_impl(cy2p_plan *plan, const T *d_X, T *d_Y, int32_
         count_launch();
         spmv_rows<T><<<(unsigned)((row_end - row_begin + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(
             row_begin, row_end, plan->d_t_indptr, plan->d_t_pairs, d_X, d_Y, nullptr, 0, nullptr);
+    } else if (B <= 16 && env_int("CY2P_ROWS_NARROW", 1)) {
+        const int rows_per_cta = 16;  // 8 warps x 2 rows
+        count_launch();
+        spmm_rows_narrow<T><<<(unsigned)((row_end - row_begin + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(
+            row_begin, row_end, plan->d_t_indptr, plan->d_t_pairs, d_X, B, d_Y);
     } else if (B % VW == 0 && aligned16(d_X) && aligned16(d_Y))
         launch_gather<T, VW>(ident, row_begin, row_end, d_X, B, d_Y, B, B, nullptr, nullptr, st);
     else
