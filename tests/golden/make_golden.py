@@ -32,8 +32,26 @@ def csr_fields(T, prefix="T_"):
             prefix + "n": np.int64(T.shape[0])}
 
 
-def golden_msm(ref, name, n, k, seed, max_iter, variable_degree=False, init="root_cells", tol=1e-5):
+def float64_matrix(g, seed):
+    """The same graph with float64 transition probabilities that are NOT float32-representable (scvelo writes float32,
+    but nothing in the reference forces it: sampling.py:40-42 then multiplies in float64 and simulation.py:24-25
+    accumulates the CDF in float64)."""
+    import scipy.sparse as sp
+
+    T = g["T"].astype(np.float64)
+    T.data = T.data * (1.0 + 0.25 * np.random.default_rng(seed + 7).random(T.nnz))
+    T = sp.csr_matrix(sp.diags(1.0 / np.asarray(T.sum(1)).ravel()) @ T)
+    T.sort_indices()
+    assert T.dtype == np.float64 and not np.array_equal(T.data.astype(np.float32).astype(np.float64), T.data)
+    g = dict(g)
+    g["T"] = T
+    return g
+
+
+def golden_msm(ref, name, n, k, seed, max_iter, variable_degree=False, init="root_cells", tol=1e-5, float64_T=False):
     g = knn_velocity_tpm(n, k=k, seed=seed, variable_degree=variable_degree)
+    if float64_T:
+        g = float64_matrix(g, seed)
     ad = adata_for(g, ref)
     init_p, _ = ref.utils.check_root_init(ad, init=init)
     stat = g["end_points"] / g["end_points"].sum()  # the reference's own fall-back (utils.py:110-112)
@@ -44,8 +62,10 @@ def golden_msm(ref, name, n, k, seed, max_iter, variable_degree=False, init="roo
     print(name, shm.shape, "conv", conv)
 
 
-def golden_chains(ref, name, n, k, seed, C, max_iter, variable_degree=False):
+def golden_chains(ref, name, n, k, seed, C, max_iter, variable_degree=False, float64_T=False):
     g = knn_velocity_tpm(n, k=k, seed=seed, variable_degree=variable_degree)
+    if float64_T:
+        g = float64_matrix(g, seed)
     ad = adata_for(g, ref)
     idx, cum = ref.simulation.extract_nonzero_entries(ad)
     rng = np.random.default_rng(seed + 100)
@@ -169,7 +189,10 @@ def main():
     jobs = [
         (golden_msm, "msm_small.npz", dict(n=400, k=10, seed=11, max_iter=120)),
         (golden_msm, "msm_vardeg.npz", dict(n=300, k=12, seed=12, max_iter=80, variable_degree=True, init="uniform")),
+        (golden_msm, "msm_f64matrix.npz", dict(n=260, k=9, seed=14, max_iter=140, variable_degree=True, float64_T=True)),
         (golden_chains, "chains_small.npz", dict(n=400, k=10, seed=11, C=48, max_iter=60)),
+        (golden_chains, "chains_f64matrix.npz", dict(n=260, k=9, seed=14, C=24, max_iter=50, variable_degree=True,
+                                                     float64_T=True)),
         (golden_chains, "chains_wide.npz", dict(n=300, k=40, seed=13, C=32, max_iter=40)),  # W > 32: multi-chunk search
         (golden_fhmm, "fhmm_restricted.npz", dict(S=4, L=3, N=60, I=25, restricted=True, seed=21)),
         (golden_fhmm, "fhmm_unrestricted.npz", dict(S=3, L=2, N=50, I=20, restricted=False, seed=22)),

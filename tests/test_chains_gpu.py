@@ -27,7 +27,7 @@ class Duck:
         return copy.deepcopy(self)
 
 
-@pytest.mark.parametrize("name", ["chains_small.npz", "chains_wide.npz"])
+@pytest.mark.parametrize("name", ["chains_small.npz", "chains_wide.npz", "chains_f64matrix.npz"])
 def test_tables_and_paths_bit_exact_vs_reference_golden(golden, name):
     import cy2path_b200 as c2p
 

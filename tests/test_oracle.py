@@ -9,7 +9,7 @@ from oracle import fhmm as ofhmm
 from oracle import msm as omsm
 
 
-@pytest.mark.parametrize("name", ["msm_small.npz", "msm_vardeg.npz"])
+@pytest.mark.parametrize("name", ["msm_small.npz", "msm_vardeg.npz", "msm_f64matrix.npz"])
 def test_msm_oracle_matches_reference_bitwise(golden, name):
     g = golden(name)
     _, hist, conv, _ = omsm.iterate_state_probability(g["T"], g["init"], g["stationary"],
@@ -45,7 +45,7 @@ def test_convergence_criteria_quirks():
     assert omsm.check_convergence_criteria(eps, 1e-5) == 5
 
 
-@pytest.mark.parametrize("name", ["chains_small.npz", "chains_wide.npz"])
+@pytest.mark.parametrize("name", ["chains_small.npz", "chains_wide.npz", "chains_f64matrix.npz"])
 def test_chain_oracle_matches_reference_bitwise(golden, name):
     g = golden(name)
     idx, cum = ochains.extract_nonzero_entries(g["T"])

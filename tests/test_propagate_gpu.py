@@ -33,7 +33,7 @@ def _assert_close(a, b):
     assert omsm.rel_l1(a, b) <= REL_L1
 
 
-@pytest.mark.parametrize("name", ["msm_small.npz", "msm_vardeg.npz"])
+@pytest.mark.parametrize("name", ["msm_small.npz", "msm_vardeg.npz", "msm_f64matrix.npz"])
 def test_history_matches_reference_golden(golden, name):
     import cy2path_b200 as c2p
 
