@@ -29,7 +29,9 @@
 extern "C" {
 #endif
 
-#define CY2P_ABI_VERSION 1
+/* 2: round-2 additions, all additive (cy2p_propagate_x*, cy2p_plan_create_host_f64, cy2p_order_host, cy2p_xbarrier,
+ * cy2p_propagate_rows_persist*); every version-1 entry point keeps its signature and meaning. */
+#define CY2P_ABI_VERSION 2
 
 enum cy2p_status {
     CY2P_OK = 0,

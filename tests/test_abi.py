@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.cy2p_abi_version() == 1
+    assert lib.cy2p_abi_version() == 2
     assert isinstance(lib.cy2p_last_error(), bytes)
 
 
